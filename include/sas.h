@@ -1,0 +1,152 @@
+/*
+ * sas.h -- C ABI of libsas_b200.so, the B200 (sm_100a) splat renderer.
+ *
+ * This is the drop-in boundary for sim_a_splat's per-step splat render.  The
+ * reference has no FFI of its own on this path: it reaches its renderers
+ * through Python object protocols (all citations are /root/reference/...):
+ *
+ *   - gsplat side:  pipeline.model.get_outputs_for_camera(cameras, obb_box)
+ *                   sim_a_splat/ns_utils/nerfstudio_utils.py:166-172
+ *   - viser side:   server.scene.add_gaussian_splats(...)      sim_a_splat/splat/splat_handler.py:106-119, :134-141
+ *                   handle.wxyz / handle.position setters       sim_a_splat/splat/splat_handler.py:283-288
+ *                   client.get_render(height,width,wxyz,position)
+ *                                                               sim_a_splat/env/splat/splat_env_wrapper.py:148-157,
+ *                                                               sim_a_splat/splat/splat_handler.py:339-344
+ *
+ * Each entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; no C++ exceptions, torch or Python objects cross it.
+ * All functions return SAS_OK (0) or a negative SAS_E* code; sas_last_error()
+ * gives the text.  All device work is enqueued on the caller's stream (a
+ * cudaStream_t passed as void*; NULL = legacy default stream); nothing
+ * synchronises except where stated.  One renderer per device; calls on one
+ * renderer are not re-entrant; renderers on different devices are independent.
+ * There is NO CPU fallback: every entry point fails with SAS_ECUDA when no
+ * CUDA device is usable.
+ */
+#ifndef SAS_H_
+#define SAS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAS_OK 0
+#define SAS_EINVAL (-1)   /* bad argument                                             */
+#define SAS_ECUDA (-2)    /* CUDA runtime error (text in sas_last_error)               */
+#define SAS_ENOMEM (-3)   /* allocation failed                                         */
+#define SAS_ECAPACITY (-4)/* intersections / images / envs exceed the configured caps  */
+#define SAS_ESTATE (-5)   /* call order (e.g. render before set_cameras)               */
+
+#define SAS_MEM_HOST 0
+#define SAS_MEM_DEVICE 1
+
+#define SAS_TILE 16
+
+typedef struct sas_renderer sas_renderer; /* opaque */
+
+/*
+ * Scene in canonical order: background Gaussians (original index order)
+ * followed by the copies of link 0..L-1 (splat_handler.py:104-143).  Values are
+ * the ACTIVATED parameters the reference's loader exposes
+ * (sim_a_splat/splat/splat_utils.py:33-45: scales=exp(.), opacities=sigmoid(.)),
+ * plus the SH coefficients gsplat consumes (features_dc ++ features_rest).
+ * The library copies everything; the caller keeps ownership of its buffers.
+ */
+typedef struct {
+    int32_t n_gaussians;
+    int32_t sh_degree;      /* 0..3 */
+    int32_t n_links;        /* L; link ids are 0..L-1 */
+    int32_t mem;            /* SAS_MEM_HOST or SAS_MEM_DEVICE: where the arrays below live */
+    const float *means;     /* [N,3] */
+    const float *quats;     /* [N,4] wxyz, as stored (normalised by the kernel) */
+    const float *scales;    /* [N,3] linear */
+    const float *opacities; /* [N]   linear */
+    const float *sh;        /* [N,(d+1)^2,3] */
+    const int32_t *link_id; /* [N]   -1 = background */
+} sas_scene_desc;
+
+typedef struct {
+    int32_t max_images;     /* I cap per render call                                  */
+    int32_t max_envs;       /* E cap                                                  */
+    int32_t max_width;      /* <= 4080 (tile coordinates are packed in 8 bits)        */
+    int32_t max_height;
+    int64_t max_isects;     /* M cap (tile intersections per render call); 0 = auto   */
+} sas_config;
+
+/* Output buffers of one render call.  Any pointer may be NULL (not produced). */
+typedef struct {
+    int32_t mem;            /* SAS_MEM_HOST (pinned or pageable; copied D2H, then the  */
+                            /* stream is synchronised) or SAS_MEM_DEVICE               */
+    int32_t nerfstudio_post;/* 1: apply splatfacto get_outputs post-processing:        */
+                            /*    rgb=clamp(rgb+(1-alpha)*background,0,1) and          */
+                            /*    depth=where(alpha>0,depth,max(depth))  (the          */
+                            /*    GaussianSplat.render contract, nerfstudio_utils.py:123-177) */
+    float background[3];    /* composited behind the splats                           */
+    float *rgb;             /* [I,H,W,3] f32                                          */
+    float *depth;           /* [I,H,W]   f32 expected depth (z along the optical axis,
+                               the convention of nerfstudio_utils.py:441-452)          */
+    float *alpha;           /* [I,H,W]   f32 accumulation                              */
+    uint8_t *rgb_u8;        /* [I,H,W,3] u8 = floor(clamp(rgb,0,1)*255+0.5): what
+                               client.get_render returns (splat_env_wrapper.py:148-157) */
+    int32_t *n_contrib;     /* [I,H,W]   Gaussians accumulated per pixel (diagnostic)  */
+} sas_outputs;
+
+typedef struct {
+    int64_t n_isects;       /* M of the last render                                    */
+    int64_t n_visible;      /* (image,gaussian) pairs with radii > 0                   */
+    int64_t max_tile_list;  /* longest (image,tile) list                               */
+    int32_t overflow;       /* 1 if M exceeded max_isects (frame is incomplete)        */
+    int32_t n_images, n_gaussians, width, height, tile_w, tile_h;
+} sas_stats;
+
+/* Replaces: GSplatLoader -> SplatHandler._load_saved_splats + _add_robot_segmented_splats +
+ * _setup_scene_splat (splat_handler.py:85-143), i.e. "upload the scene to the renderer". */
+int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, sas_renderer **out);
+void sas_destroy(sas_renderer *r);
+
+/* Replaces: the per-link `handle.wxyz = ...; handle.position = ...` writes of
+ * SplatHandler.draw_handler (splat_handler.py:283-288), batched over envs.
+ * poses [n_envs, L, 12] fp32 = (rot row-major 3x3 | pos), meaning
+ * mu' = rot*mu + pos, Sigma' = rot*Sigma*rot^T for every Gaussian of link l. */
+int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem, void *stream);
+
+/* Replaces: the (height,width,wxyz,position) arguments of client.get_render
+ * (splat_env_wrapper.py:148-157) / the Cameras(...) built in GaussianSplat.render
+ * (nerfstudio_utils.py:125-138), batched.  HOST pointers.  viewmats [I,16] are
+ * world->camera, row-major, OpenCV axes (+z forward); Ks [I,9] row-major;
+ * env_of_image [I] selects the env whose link poses image i uses (NULL = all 0). */
+int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, const int32_t *env_of_image,
+                    int n_images, int width, int height, void *stream);
+
+/* Replaces: client.get_render(...) per camera (splat_env_wrapper.py:147-158) and
+ * model.get_outputs_for_camera (nerfstudio_utils.py:166-172): renders every image
+ * set by sas_set_cameras with the current link poses. */
+int sas_render(sas_renderer *r, const sas_outputs *out, void *stream);
+
+/* Grow the intersection buffers (pairs, sorted ids) to hold max_isects entries.  A render whose
+ * intersection count exceeded the capacity sets sas_stats.overflow; reserve more and re-render. */
+int sas_reserve_isects(sas_renderer *r, long long max_isects);
+
+/* Synchronises the device. */
+int sas_get_stats(sas_renderer *r, sas_stats *out);
+
+/* Intermediates of the last render, for parity tests (synchronises). */
+#define SAS_DBG_RECORDS 1   /* [I,N,12] f32: m2x,m2y,0.5*conic_a,conic_b, 0.5*conic_c,opacity,radius_x,radius_y, r,g,b,depth */
+#define SAS_DBG_BINS 2      /* [I,N,2] u32: (x0 | y0<<8 | x1<<16 | y1<<24), bits(depth); tile rect, exclusive max */
+#define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of per-(image,tile) counts          */
+#define SAS_DBG_SORTED_GIDS 4  /* [M] i32 Gaussian index per intersection, (image,tile,depth,gid) order */
+int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
+
+/* Number of kernels the last sas_render enqueued (for bench.py's gpu_launches). */
+int sas_last_launch_count(const sas_renderer *r);
+
+const char *sas_last_error(const sas_renderer *r); /* r may be NULL: error of the last failed sas_create */
+const char *sas_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAS_H_ */

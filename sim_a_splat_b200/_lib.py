@@ -1,0 +1,104 @@
+"""ctypes binding of libsas_b200.so -- the C ABI declared in include/sas.h.
+
+The product path has no CPU fallback: if the shared library is missing it is
+built in-tree with nvcc (sim_a_splat_b200/_build.py); if that fails, or no CUDA
+device is usable, the failure is raised, never papered over.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _build
+
+SAS_OK = 0
+SAS_MEM_HOST = 0
+SAS_MEM_DEVICE = 1
+SAS_DBG_RECORDS = 1
+SAS_DBG_BINS = 2
+SAS_DBG_TILE_OFFSETS = 3
+SAS_DBG_SORTED_GIDS = 4
+
+EXPORTS = [
+    "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
+    "sas_get_stats", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
+]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("n_gaussians", C.c_int32), ("sh_degree", C.c_int32), ("n_links", C.c_int32), ("mem", C.c_int32),
+                ("means", C.c_void_p), ("quats", C.c_void_p), ("scales", C.c_void_p), ("opacities", C.c_void_p),
+                ("sh", C.c_void_p), ("link_id", C.c_void_p)]
+
+
+class Config(C.Structure):
+    _fields_ = [("max_images", C.c_int32), ("max_envs", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
+                ("max_isects", C.c_int64)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("mem", C.c_int32), ("nerfstudio_post", C.c_int32), ("background", C.c_float * 3),
+                ("rgb", C.c_void_p), ("depth", C.c_void_p), ("alpha", C.c_void_p), ("rgb_u8", C.c_void_p),
+                ("n_contrib", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_isects", C.c_int64), ("n_visible", C.c_int64), ("max_tile_list", C.c_int64), ("overflow", C.c_int32),
+                ("n_images", C.c_int32), ("n_gaussians", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
+
+
+class SasError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsas_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def library_path() -> Path:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if needed) libsas_b200.so and declare the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build_library()
+    if not _build.LIB.exists():
+        raise RuntimeError(f"{_build.LIB} is missing and could not be built; sim_a_splat_b200 has no CPU fallback")
+    lib = C.CDLL(str(_build.LIB))
+    P = C.c_void_p
+    lib.sas_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(Config), C.c_int, C.POINTER(P)]
+    lib.sas_create.restype = C.c_int
+    lib.sas_destroy.argtypes = [P]
+    lib.sas_destroy.restype = None
+    lib.sas_set_link_poses.argtypes = [P, P, C.c_int, C.c_int, P]
+    lib.sas_set_link_poses.restype = C.c_int
+    lib.sas_set_cameras.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, P]
+    lib.sas_set_cameras.restype = C.c_int
+    lib.sas_render.argtypes = [P, C.POINTER(Outputs), P]
+    lib.sas_render.restype = C.c_int
+    lib.sas_reserve_isects.argtypes = [P, C.c_longlong]
+    lib.sas_reserve_isects.restype = C.c_int
+    lib.sas_get_stats.argtypes = [P, C.POINTER(Stats)]
+    lib.sas_get_stats.restype = C.c_int
+    lib.sas_debug_fetch.argtypes = [P, C.c_int, P, C.c_size_t]
+    lib.sas_debug_fetch.restype = C.c_int
+    lib.sas_last_launch_count.argtypes = [P]
+    lib.sas_last_launch_count.restype = C.c_int
+    lib.sas_last_error.argtypes = [P]
+    lib.sas_last_error.restype = C.c_char_p
+    lib.sas_version.argtypes = []
+    lib.sas_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, code: int) -> None:
+    if code != SAS_OK:
+        msg = lib.sas_last_error(handle)
+        raise SasError(code, msg.decode() if msg else "")

@@ -1,0 +1,375 @@
+// sas_api.cu -- C ABI of libsas_b200.so (see include/sas.h for the contract and the reference
+// interfaces each entry point replaces).  Host-side only: buffer management, camera packing,
+// kernel sequencing on the caller's stream.  No CPU fallback exists: without a usable CUDA
+// device every entry point fails with SAS_ECUDA.
+#include "../../include/sas.h"
+#include "sas_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct sas_renderer {
+    int device = 0;
+    int N = 0, n_pad = 0, sh_degree = 0, L = 0;
+    sas_config cfg{};
+    std::string err;
+    // scene (SoA)
+    float4 *mean_op = nullptr, *quat = nullptr, *scale_link = nullptr;
+    float *sh_planes = nullptr;
+    // per-call state
+    float *link_poses = nullptr;
+    int n_envs = 0;
+    SasCamera *cams = nullptr;
+    SasCamera *cams_host = nullptr;  // pinned staging
+    cudaEvent_t cams_copied = nullptr;
+    int I = 0, W = 0, H = 0, tile_w = 0, tile_h = 0;
+    bool cameras_set = false;
+    // grow-only work buffers
+    DevBuf rec, bins, tile_count, tile_cursor, tile_offset, block_sums, pairs, pairs_alt, sorted_gid, img_max;
+    DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
+    long long max_isects = 0;
+    SasCounters *counters = nullptr;
+    bool rendered = false;
+    int last_launches = 0;
+};
+
+namespace {
+
+int fail(sas_renderer *r, int code, const std::string &msg) {
+    if (r) r->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define SAS_CUDA(r, call)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            char buf_[512];                                                                                \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail((r), e_ == cudaErrorMemoryAllocation ? SAS_ENOMEM : SAS_ECUDA, buf_);              \
+        }                                                                                                  \
+    } while (0)
+
+int ensure(sas_renderer *r, DevBuf &b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return SAS_OK;
+    if (b.p) {
+        SAS_CUDA(r, cudaDeviceSynchronize());
+        SAS_CUDA(r, cudaFree(b.p));
+        b.p = nullptr; b.bytes = 0;
+    }
+    if (bytes == 0) bytes = 16;
+    SAS_CUDA(r, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return SAS_OK;
+}
+
+void free_buf(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+}
+
+int ensure_isects(sas_renderer *r, long long m) {
+    if (m > 0x7ffffff0ll) m = 0x7ffffff0ll;
+    if (m <= r->max_isects && r->pairs.p) return SAS_OK;
+    int rc;
+    if ((rc = ensure(r, r->pairs, (size_t)m * sizeof(uint2)))) return rc;
+    if ((rc = ensure(r, r->pairs_alt, (size_t)m * sizeof(uint2)))) return rc;
+    if ((rc = ensure(r, r->sorted_gid, (size_t)m * sizeof(int)))) return rc;
+    r->max_isects = m;
+    return SAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sas_version(void) { return "sas_b200 0.1.0 (sm_100a)"; }
+
+const char *sas_last_error(const sas_renderer *r) { return r ? r->err.c_str() : g_create_error.c_str(); }
+
+int sas_last_launch_count(const sas_renderer *r) { return r ? r->last_launches : 0; }
+
+int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, sas_renderer **out) {
+    if (!scene || !cfg || !out) return fail(nullptr, SAS_EINVAL, "sas_create: null argument");
+    *out = nullptr;
+    if (scene->n_gaussians <= 0 || scene->sh_degree < 0 || scene->sh_degree > 3 || scene->n_links < 0 || !scene->means ||
+        !scene->quats || !scene->scales || !scene->opacities || !scene->sh)
+        return fail(nullptr, SAS_EINVAL, "sas_create: bad scene descriptor");
+    if (cfg->max_width > 4080 || cfg->max_height > 4080 || cfg->max_images <= 0 || cfg->max_images > 65535)
+        return fail(nullptr, SAS_EINVAL, "sas_create: max_width/max_height must be <= 4080 and 0 < max_images <= 65535");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "sas_create: no usable CUDA device %d (%s); there is no CPU fallback", device,
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return fail(nullptr, SAS_ECUDA, buf);
+    }
+    sas_renderer *r = new sas_renderer();
+    r->device = device;
+    r->cfg = *cfg;
+    const int N = scene->n_gaussians, K = (scene->sh_degree + 1) * (scene->sh_degree + 1);
+    r->N = N; r->sh_degree = scene->sh_degree; r->L = scene->n_links;
+    r->n_pad = (N + 31) & ~31;
+    auto bail = [&](int code) { std::string m = r->err; sas_destroy(r); g_create_error = m; return code; };
+#define SAS_TRY(x) do { int rc_ = (x); if (rc_) return bail(rc_); } while (0)
+#define SAS_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { r->err = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? SAS_ENOMEM : SAS_ECUDA); } } while (0)
+    SAS_CUDA_C(cudaSetDevice(device));
+
+    // bring the scene to the host if needed, pack SoA, upload
+    std::vector<float> h_means((size_t)N * 3), h_quats((size_t)N * 4), h_scales((size_t)N * 3), h_op(N), h_sh((size_t)N * K * 3);
+    std::vector<int32_t> h_link(N, -1);
+    const cudaMemcpyKind kind = scene->mem == SAS_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+    SAS_CUDA_C(cudaMemcpy(h_means.data(), scene->means, h_means.size() * 4, kind));
+    SAS_CUDA_C(cudaMemcpy(h_quats.data(), scene->quats, h_quats.size() * 4, kind));
+    SAS_CUDA_C(cudaMemcpy(h_scales.data(), scene->scales, h_scales.size() * 4, kind));
+    SAS_CUDA_C(cudaMemcpy(h_op.data(), scene->opacities, h_op.size() * 4, kind));
+    SAS_CUDA_C(cudaMemcpy(h_sh.data(), scene->sh, h_sh.size() * 4, kind));
+    if (scene->link_id) SAS_CUDA_C(cudaMemcpy(h_link.data(), scene->link_id, (size_t)N * 4, kind));
+    for (int g = 0; g < N; g++)
+        if (h_link[g] >= scene->n_links) { r->err = "sas_create: link_id out of range"; return bail(SAS_EINVAL); }
+
+    std::vector<float4> p_mean(N), p_quat(N), p_scale(N);
+    std::vector<float> p_sh((size_t)K * 3 * r->n_pad, 0.0f);
+    for (int g = 0; g < N; g++) {
+        p_mean[g] = make_float4(h_means[3 * g], h_means[3 * g + 1], h_means[3 * g + 2], h_op[g]);
+        p_quat[g] = make_float4(h_quats[4 * g], h_quats[4 * g + 1], h_quats[4 * g + 2], h_quats[4 * g + 3]);
+        float lid;
+        int32_t li = h_link[g] < 0 ? -1 : h_link[g];
+        memcpy(&lid, &li, 4);
+        p_scale[g] = make_float4(h_scales[3 * g], h_scales[3 * g + 1], h_scales[3 * g + 2], lid);
+        for (int k = 0; k < K; k++)
+            for (int ch = 0; ch < 3; ch++) p_sh[(size_t)(3 * k + ch) * r->n_pad + g] = h_sh[((size_t)g * K + k) * 3 + ch];
+    }
+    SAS_CUDA_C(cudaMalloc(&r->mean_op, sizeof(float4) * N));
+    SAS_CUDA_C(cudaMalloc(&r->quat, sizeof(float4) * N));
+    SAS_CUDA_C(cudaMalloc(&r->scale_link, sizeof(float4) * N));
+    SAS_CUDA_C(cudaMalloc(&r->sh_planes, sizeof(float) * p_sh.size()));
+    SAS_CUDA_C(cudaMemcpy(r->mean_op, p_mean.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
+    SAS_CUDA_C(cudaMemcpy(r->quat, p_quat.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
+    SAS_CUDA_C(cudaMemcpy(r->scale_link, p_scale.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
+    SAS_CUDA_C(cudaMemcpy(r->sh_planes, p_sh.data(), sizeof(float) * p_sh.size(), cudaMemcpyHostToDevice));
+
+    const int maxE = cfg->max_envs > 0 ? cfg->max_envs : 1;
+    if (r->L > 0) SAS_CUDA_C(cudaMalloc(&r->link_poses, sizeof(float) * 12 * (size_t)maxE * r->L));
+    SAS_CUDA_C(cudaMalloc(&r->cams, sizeof(SasCamera) * cfg->max_images));
+    SAS_CUDA_C(cudaMallocHost(&r->cams_host, sizeof(SasCamera) * cfg->max_images));
+    SAS_CUDA_C(cudaEventCreateWithFlags(&r->cams_copied, cudaEventDisableTiming));
+    SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters)));
+    SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters)));
+    long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
+    SAS_TRY(ensure_isects(r, m));
+#undef SAS_TRY
+#undef SAS_CUDA_C
+    *out = r;
+    return SAS_OK;
+}
+
+void sas_destroy(sas_renderer *r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaDeviceSynchronize();
+    cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
+    cudaFree(r->link_poses); cudaFree(r->cams); cudaFree(r->counters);
+    if (r->cams_host) cudaFreeHost(r->cams_host);
+    if (r->cams_copied) cudaEventDestroy(r->cams_copied);
+    DevBuf *bufs[] = {&r->rec, &r->bins, &r->tile_count, &r->tile_cursor, &r->tile_offset, &r->block_sums, &r->pairs, &r->pairs_alt,
+                      &r->sorted_gid, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc};
+    for (DevBuf *b : bufs) free_buf(*b);
+    delete r;
+}
+
+int sas_reserve_isects(sas_renderer *r, long long max_isects) {
+    if (!r || max_isects <= 0) return fail(r, SAS_EINVAL, "sas_reserve_isects: bad argument");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    return ensure_isects(r, max_isects);
+}
+
+int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem, void *stream) {
+    if (!r) return SAS_EINVAL;
+    if (r->L == 0) return SAS_OK;
+    if (!poses || n_envs <= 0) return fail(r, SAS_EINVAL, "sas_set_link_poses: null poses or n_envs <= 0");
+    const int maxE = r->cfg.max_envs > 0 ? r->cfg.max_envs : 1;
+    if (n_envs > maxE) return fail(r, SAS_ECAPACITY, "sas_set_link_poses: n_envs exceeds max_envs");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaMemcpyAsync(r->link_poses, poses, sizeof(float) * 12 * (size_t)n_envs * r->L,
+                                mem == SAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    r->n_envs = n_envs;
+    return SAS_OK;
+}
+
+int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, const int32_t *env_of_image, int n_images,
+                    int width, int height, void *stream) {
+    if (!r) return SAS_EINVAL;
+    if (!viewmats || !Ks || n_images <= 0 || width <= 0 || height <= 0) return fail(r, SAS_EINVAL, "sas_set_cameras: bad argument");
+    if (n_images > r->cfg.max_images) return fail(r, SAS_ECAPACITY, "sas_set_cameras: n_images exceeds max_images");
+    if (width > r->cfg.max_width || height > r->cfg.max_height || width > 4080 || height > 4080)
+        return fail(r, SAS_ECAPACITY, "sas_set_cameras: image size exceeds max_width/max_height");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaEventSynchronize(r->cams_copied));  // previous staging copy finished
+    for (int i = 0; i < n_images; i++) {
+        const float *vm = viewmats + 16 * (size_t)i;
+        const float *K = Ks + 9 * (size_t)i;
+        SasCamera &c = r->cams_host[i];
+        for (int k = 0; k < 12; k++) c.vm[k] = vm[k];
+        c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+        // camera origin -R^T t in fp64, rounded once (the oracle does the same on the same fp32 viewmat)
+        for (int a = 0; a < 3; a++) {
+            double s = 0.0;
+            for (int b = 0; b < 3; b++) s += (double)vm[4 * b + a] * (double)vm[4 * b + 3];
+            c.campos[a] = (float)(-s);
+        }
+        const int env = env_of_image ? env_of_image[i] : 0;
+        if (env < 0 || (r->L > 0 && env >= (r->cfg.max_envs > 0 ? r->cfg.max_envs : 1)))
+            return fail(r, SAS_EINVAL, "sas_set_cameras: env_of_image out of range");
+        c.env = env;
+        {   // same fp32 operation sequence as oracle/splat_oracle.c:project_one (host code is built
+            // with -ffp-contract=off, SSE fp32: every operation individually rounded)
+            const volatile float Wf = (float)width, Hf = (float)height;
+            const volatile float tan_fovx = 0.5f * Wf / c.fx, tan_fovy = 0.5f * Hf / c.fy;
+            const volatile float ax = 0.3f * tan_fovx, ay = 0.3f * tan_fovy;
+            c.lim_x_pos = (Wf - c.cx) / c.fx + ax;
+            c.lim_x_neg = c.cx / c.fx + ax;
+            c.lim_y_pos = (Hf - c.cy) / c.fy + ay;
+            c.lim_y_neg = c.cy / c.fy + ay;
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SAS_CUDA(r, cudaMemcpyAsync(r->cams, r->cams_host, sizeof(SasCamera) * n_images, cudaMemcpyHostToDevice, st));
+    SAS_CUDA(r, cudaEventRecord(r->cams_copied, st));
+    r->I = n_images; r->W = width; r->H = height;
+    r->tile_w = (width + SAS_TILE - 1) / SAS_TILE;
+    r->tile_h = (height + SAS_TILE - 1) / SAS_TILE;
+    r->cameras_set = true;
+    // size the grow-only work buffers for this shape
+    const size_t IN = (size_t)n_images * r->N, IT = (size_t)n_images * r->tile_w * r->tile_h;
+    int rc;
+    if ((rc = ensure(r, r->rec, IN * sizeof(SasRecord)))) return rc;
+    if ((rc = ensure(r, r->bins, IN * sizeof(uint2)))) return rc;
+    if ((rc = ensure(r, r->tile_count, IT * 4))) return rc;
+    if ((rc = ensure(r, r->tile_cursor, IT * 4))) return rc;
+    if ((rc = ensure(r, r->tile_offset, (IT + 1) * 4))) return rc;
+    if ((rc = ensure(r, r->block_sums, (IT / 1024 + 2) * 4))) return rc;
+    if ((rc = ensure(r, r->img_max, (size_t)n_images * 4))) return rc;
+    return SAS_OK;
+}
+
+int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
+    if (!r || !out) return SAS_EINVAL;
+    if (!r->cameras_set) return fail(r, SAS_ESTATE, "sas_render: sas_set_cameras has not been called");
+    if (r->L > 0 && r->n_envs == 0) return fail(r, SAS_ESTATE, "sas_render: scene has links but sas_set_link_poses has not been called");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int I = r->I, W = r->W, H = r->H, tw = r->tile_w, th = r->tile_h, N = r->N;
+    const size_t IT = (size_t)I * tw * th, P = (size_t)I * W * H;
+    int launches = 0;
+
+    float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
+    uint8_t *d_u8 = out->rgb_u8;
+    int *d_nc = out->n_contrib;
+    const bool host_out = out->mem == SAS_MEM_HOST;
+    const bool ns = out->nerfstudio_post != 0;
+    int rc;
+    if (host_out) {
+        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
+        if (out->depth) { if ((rc = ensure(r, r->o_depth, P * 4))) return rc; d_depth = (float *)r->o_depth.p; }
+        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
+        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8, P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8.p; }
+        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc, P * 4))) return rc; d_nc = (int *)r->o_nc.p; }
+    } else if (ns) {
+        if (!d_rgb) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
+        if (!d_alpha) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
+    }
+
+    SAS_CUDA(r, cudaMemsetAsync(r->tile_count.p, 0, IT * 4, st));
+    SAS_CUDA(r, cudaMemsetAsync(r->tile_cursor.p, 0, IT * 4, st));
+    SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters), st));
+
+    SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, N, r->sh_degree,
+                                   r->L > 0 ? r->link_poses : nullptr, r->L, r->cams, I, W, H, tw, th, (SasRecord *)r->rec.p,
+                                   (uint2 *)r->bins.p, (unsigned *)r->tile_count.p, r->counters, st));
+    launches += 1;
+    SAS_CUDA(r, sas_launch_scan((const unsigned *)r->tile_count.p, (int)IT, (int *)r->tile_offset.p, (unsigned *)r->block_sums.p,
+                                r->counters, r->max_isects, st, &launches));
+    SAS_CUDA(r, sas_launch_emit((const uint2 *)r->bins.p, N, I, tw, th, (const int *)r->tile_offset.p, (unsigned *)r->tile_cursor.p,
+                                (uint2 *)r->pairs.p, r->max_isects, st));
+    launches += 1;
+    SAS_CUDA(r, sas_launch_tile_sort((uint2 *)r->pairs.p, (uint2 *)r->pairs_alt.p, (const int *)r->tile_offset.p, (int)IT,
+                                     (int *)r->sorted_gid.p, r->max_isects, st, &launches));
+    // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
+    const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
+    SAS_CUDA(r, sas_launch_composite((const SasRecord *)r->rec.p, (const int *)r->sorted_gid.p, (const int *)r->tile_offset.p, N, I, W,
+                                     H, tw, th, b0, b1, b2, d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, st));
+    launches += 1;
+    if (ns) {
+        SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, I, W, H, out->background[0], out->background[1],
+                                       out->background[2], (unsigned *)r->img_max.p, st, &launches));
+    }
+    r->last_launches = launches;
+    r->rendered = true;
+    if (host_out) {
+        if (out->rgb) SAS_CUDA(r, cudaMemcpyAsync(out->rgb, d_rgb, P * 12, cudaMemcpyDeviceToHost, st));
+        if (out->depth) SAS_CUDA(r, cudaMemcpyAsync(out->depth, d_depth, P * 4, cudaMemcpyDeviceToHost, st));
+        if (out->alpha) SAS_CUDA(r, cudaMemcpyAsync(out->alpha, d_alpha, P * 4, cudaMemcpyDeviceToHost, st));
+        if (out->rgb_u8) SAS_CUDA(r, cudaMemcpyAsync(out->rgb_u8, d_u8, P * 3, cudaMemcpyDeviceToHost, st));
+        if (out->n_contrib) SAS_CUDA(r, cudaMemcpyAsync(out->n_contrib, d_nc, P * 4, cudaMemcpyDeviceToHost, st));
+        SAS_CUDA(r, cudaStreamSynchronize(st));
+    }
+    return SAS_OK;
+}
+
+int sas_get_stats(sas_renderer *r, sas_stats *out) {
+    if (!r || !out) return SAS_EINVAL;
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaDeviceSynchronize());
+    SasCounters c;
+    SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->n_isects = (int64_t)c.n_isects;
+    out->n_visible = (int64_t)c.n_visible;
+    out->max_tile_list = (int64_t)c.max_tile_list;
+    out->overflow = (int32_t)c.overflow;
+    out->n_images = r->I; out->n_gaussians = r->N; out->width = r->W; out->height = r->H;
+    out->tile_w = r->tile_w; out->tile_h = r->tile_h;
+    return SAS_OK;
+}
+
+int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
+    if (!r || !dst_host) return SAS_EINVAL;
+    if (!r->rendered) return fail(r, SAS_ESTATE, "sas_debug_fetch: nothing rendered yet");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaDeviceSynchronize());
+    const size_t IN = (size_t)r->I * r->N, IT = (size_t)r->I * r->tile_w * r->tile_h;
+    const void *src = nullptr;
+    size_t avail = 0;
+    switch (what) {
+        case SAS_DBG_RECORDS: src = r->rec.p; avail = IN * sizeof(SasRecord); break;
+        case SAS_DBG_BINS: src = r->bins.p; avail = IN * sizeof(uint2); break;
+        case SAS_DBG_TILE_OFFSETS: src = r->tile_offset.p; avail = (IT + 1) * 4; break;
+        case SAS_DBG_SORTED_GIDS: {
+            SasCounters c;
+            SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
+            long long m = (long long)c.n_isects < r->max_isects ? (long long)c.n_isects : r->max_isects;
+            src = r->sorted_gid.p; avail = (size_t)m * 4;
+            break;
+        }
+        default: return fail(r, SAS_EINVAL, "sas_debug_fetch: unknown item");
+    }
+    if (bytes > avail) return fail(r, SAS_EINVAL, "sas_debug_fetch: more bytes requested than available");
+    if (bytes) SAS_CUDA(r, cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost));
+    return SAS_OK;
+}
+
+}  // extern "C"

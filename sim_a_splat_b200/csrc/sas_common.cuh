@@ -1,0 +1,97 @@
+// sas_common.cuh -- shared device structs and helpers of libsas_b200 (sm_100a).
+//
+// Numerics contract (see DESIGN.md "Numerics"): this library is compiled with
+// -fmad=false, so every '*' '+' '-' '/' below is one individually rounded IEEE
+// binary32 operation in the order written; a fused multiply-add happens only
+// where fmaf() is written.  sqrtf and '/' are IEEE (nvcc defaults, no
+// --use_fast_math).  No hardware approximation (ex2.approx, rsqrt, rcp) is used
+// anywhere that feeds an integer decision (radii, tile ids, depth keys, the
+// alpha / transmittance tests).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SAS_TILE_PX 16
+#define SAS_EPS2D 0.3f
+#define SAS_NEAR 0.01f
+#define SAS_FAR 1e10f
+#define SAS_EXTEND 3.33f
+#define SAS_ALPHA_MIN (1.0f / 255.0f)
+#define SAS_ALPHA_MAX 0.999f
+#define SAS_T_MIN 1e-4f
+// sigma above which alpha < 1/255 for every opacity <= 1: exp(-5.55) = 3.887e-3 < 1/255 = 3.9216e-3
+// (0.9 % margin against the 2e-7 relative error of sas_exp_neg).  Pure work-skipping: the exact
+// alpha test below it is unchanged.
+#define SAS_SIGMA_SKIP 5.55f
+
+// Per-image camera block, filled on the host by sas_set_cameras.
+struct SasCamera {
+    float vm[12];     // world->camera rows 0..2 of the 4x4 (row-major): R | t
+    float fx, fy, cx, cy;
+    float campos[3];  // camera origin in world, -R^T t computed in fp64 on the host
+    int32_t env;      // env whose link poses this image uses
+    // gsplat _persp_proj clamp limits, computed once per camera on the host with the same
+    // individually rounded fp32 operations the oracle performs per Gaussian
+    float lim_x_pos, lim_x_neg, lim_y_pos, lim_y_neg;
+};
+
+// Projected Gaussian, 48 B, written per visible (image, gaussian).
+struct __align__(16) SasRecord {
+    float4 a;  // m2x, m2y, 0.5*conic_a, conic_b
+    float4 b;  // 0.5*conic_c, opacity, radius_x, radius_y
+    float4 c;  // r, g, b, depth
+};
+
+// exp(x), x <= 0.  2^(x*log2e) with a round-to-nearest split and a degree-5
+// polynomial in explicit fmaf; the exponent is added into the float's bits.
+// Bit-identical to oracle/splat_oracle.c:orc_exp_neg (same operations, same
+// order); |rel err| ~ 2e-7.  ex2.approx is not reproducible off-device, and the
+// transmittance test T*(1-alpha) <= 1e-4 must flip on the same Gaussian in both.
+__device__ __forceinline__ float sas_exp_neg(float x) {
+    float t = x * 1.44269502162933349609375f;
+    t = fmaxf(t, -125.0f);
+    float n = rintf(t);
+    float f = t - n;
+    float p = 0.001327647129073739f;
+    p = fmaf(p, f, 0.009675540961325169f);
+    p = fmaf(p, f, 0.05550713092088699f);
+    p = fmaf(p, f, 0.24022120237350464f);
+    p = fmaf(p, f, 0.6931469440460205f);
+    p = fmaf(p, f, 1.0000001192092896f);
+    return __int_as_float(__float_as_int(p) + (((int)n) << 23));
+}
+
+__device__ __forceinline__ void sas_cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sas_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sas_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Device-side counters of one render call.
+struct SasCounters {
+    unsigned long long n_isects;
+    unsigned long long n_visible;
+    unsigned int max_tile_list;
+    unsigned int overflow;
+};
+
+// Launchers (each returns the cudaError_t of the launch).
+cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
+                               int n_pad, int N, int sh_degree, const float *link_poses, int L, const SasCamera *cams,
+                               int I, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
+                               unsigned int *tile_count, SasCounters *counters, cudaStream_t st);
+cudaError_t sas_launch_scan(const unsigned int *tile_count, int n, int *tile_offset, unsigned int *block_sums,
+                            SasCounters *counters, long long max_isects, cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_emit(const uint2 *bins, int N, int I, int tile_w, int tile_h, const int *tile_offset,
+                            unsigned int *tile_cursor, uint2 *pairs, long long max_isects, cudaStream_t st);
+cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *tile_offset, int n_buckets, int *sorted_gid,
+                                 long long max_isects, cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_composite(const SasRecord *rec, const int *sorted_gid, const int *tile_offset, int N, int I, int W,
+                                 int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, float *rgb, float *depth,
+                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, cudaStream_t st);
+cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
+                               float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

@@ -1,0 +1,192 @@
+"""SplatRenderer: host-side object over the C ABI of libsas_b200.so (include/sas.h).
+
+PyTorch is plumbing here (device buffers, pinned host memory, the current CUDA
+stream); every pixel is produced by the hand-written sm_100a kernels in csrc/.
+There is no CPU or PyTorch fallback: constructing a renderer without a CUDA
+device raises.
+
+Reference interfaces this object stands behind (file:line in /root/reference):
+  * client.get_render(height,width,wxyz,position)   sim_a_splat/env/splat/splat_env_wrapper.py:148-157
+  * handle.wxyz / handle.position per link           sim_a_splat/splat/splat_handler.py:283-288
+  * model.get_outputs_for_camera(cameras, obb_box)   sim_a_splat/ns_utils/nerfstudio_utils.py:166-172
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .scene import SplatScene
+
+NS_BACKGROUND = (0.1490, 0.1647, 0.2157)  # splatfacto's eval-time colour for background_color="random" (config.yml:152)
+
+
+def _f32c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class SplatRenderer:
+    def __init__(self, scene: SplatScene, device: int = 0, max_images: int = 1, max_envs: int = 1,
+                 max_width: int = 1920, max_height: int = 1080, max_isects: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("sim_a_splat_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._torch = torch
+        self._lib = L.load()
+        self.device = int(device)
+        self.scene = scene
+        self.N, self.L = scene.N, scene.L
+        arrs = [_f32c(scene.means), _f32c(scene.quats), _f32c(scene.scales), _f32c(scene.opacities), _f32c(scene.sh),
+                np.ascontiguousarray(scene.link_id, dtype=np.int32)]
+        desc = L.SceneDesc(scene.N, scene.sh_degree, scene.L, L.SAS_MEM_HOST, *[a.ctypes.data for a in arrs])
+        cfg = L.Config(int(max_images), int(max_envs), int(max_width), int(max_height), int(max_isects))
+        h = C.c_void_p()
+        L.check(self._lib, None, self._lib.sas_create(C.byref(desc), C.byref(cfg), self.device, C.byref(h)))
+        self._h = h
+        self.max_images, self.max_envs = int(max_images), int(max_envs)
+        self.I = self.W = self.H = 0
+        self._pinned: Dict[str, "torch.Tensor"] = {}
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sas_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self, stream=None) -> C.c_void_p:
+        if stream is None:
+            stream = self._torch.cuda.current_stream(self.device)
+        return C.c_void_p(int(stream.cuda_stream))
+
+    # -- per-step inputs --------------------------------------------------------------------
+    def set_link_poses(self, poses, stream=None) -> None:
+        """poses [E,L,12] (rot row-major | pos): numpy (host) or a CUDA float32 tensor (device)."""
+        if self.L == 0:
+            return
+        torch = self._torch
+        if isinstance(poses, torch.Tensor) and poses.is_cuda:
+            p = poses.contiguous().float()
+            E = p.numel() // (self.L * 12)
+            code = self._lib.sas_set_link_poses(self._h, C.c_void_p(p.data_ptr()), E, L.SAS_MEM_DEVICE, self._stream(stream))
+            self._keep_poses = p
+        else:
+            p = _f32c(poses.cpu().numpy() if isinstance(poses, torch.Tensor) else poses).reshape(-1, self.L, 12)
+            code = self._lib.sas_set_link_poses(self._h, p.ctypes.data, p.shape[0], L.SAS_MEM_HOST, self._stream(stream))
+        L.check(self._lib, self._h, code)
+
+    def set_cameras(self, viewmats, Ks, width: int, height: int, env_of_image: Optional[Sequence[int]] = None, stream=None) -> None:
+        """viewmats [I,4,4] world->camera (OpenCV axes), Ks [I,3,3] or [3,3]; host arrays."""
+        vm = _f32c(viewmats).reshape(-1, 16)
+        I = vm.shape[0]
+        K = _f32c(Ks).reshape(-1, 9)
+        if K.shape[0] == 1 and I > 1:
+            K = np.ascontiguousarray(np.repeat(K, I, axis=0))
+        env = None
+        if env_of_image is not None:
+            env = np.ascontiguousarray(env_of_image, dtype=np.int32)
+            assert env.shape == (I,)
+        code = self._lib.sas_set_cameras(self._h, vm.ctypes.data, K.ctypes.data, env.ctypes.data if env is not None else None,
+                                         I, int(width), int(height), self._stream(stream))
+        L.check(self._lib, self._h, code)
+        self.I, self.W, self.H = I, int(width), int(height)
+
+    # -- render -----------------------------------------------------------------------------
+    def _alloc(self, name: str, to_host: bool):
+        torch = self._torch
+        I, H, W = self.I, self.H, self.W
+        shape, dt = {"rgb": ((I, H, W, 3), torch.float32), "depth": ((I, H, W), torch.float32),
+                     "alpha": ((I, H, W), torch.float32), "rgb_u8": ((I, H, W, 3), torch.uint8),
+                     "n_contrib": ((I, H, W), torch.int32)}[name]
+        if to_host:
+            t = self._pinned.get(name)
+            if t is None or tuple(t.shape) != shape:
+                t = torch.empty(shape, dtype=dt, pin_memory=True)
+                self._pinned[name] = t
+            return t
+        return torch.empty(shape, dtype=dt, device=f"cuda:{self.device}")
+
+    def render(self, outputs: Iterable[str] = ("rgb", "depth", "alpha"), background=(0.0, 0.0, 0.0),
+               nerfstudio_post: bool = False, to_host: bool = False, out: Optional[dict] = None, stream=None,
+               check: bool = True) -> dict:
+        """Render every image set by set_cameras.  Returns {name: torch tensor}: CUDA tensors, or (to_host=True)
+        pinned host tensors filled by a D2H copy inside the call (which then synchronises the stream).
+        check=True reads the device counters afterwards (a sync) and transparently grows the intersection
+        buffers and re-renders if they overflowed."""
+        if self.I == 0:
+            raise RuntimeError("set_cameras has not been called")
+        names = list(outputs)
+        bufs = dict(out) if out else {}
+        for n in names:
+            if n not in bufs:
+                bufs[n] = self._alloc(n, to_host)
+        o = L.Outputs()
+        o.mem = L.SAS_MEM_HOST if to_host else L.SAS_MEM_DEVICE
+        o.nerfstudio_post = 1 if nerfstudio_post else 0
+        o.background = (C.c_float * 3)(*[float(b) for b in background])
+        for n in ("rgb", "depth", "alpha", "rgb_u8", "n_contrib"):
+            setattr(o, n, C.c_void_p(bufs[n].data_ptr()) if n in bufs else None)
+        st = self._stream(stream)
+        L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
+        if check:
+            s = self.stats()
+            if s["overflow"]:
+                L.check(self._lib, self._h, self._lib.sas_reserve_isects(self._h, int(s["n_isects"] * 1.25) + 1024))
+                L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
+                if self.stats()["overflow"]:
+                    raise L.SasError(-4, "intersection buffers overflowed twice")
+        return {n: bufs[n] for n in names}
+
+    def reserve_isects(self, n: int) -> None:
+        L.check(self._lib, self._h, self._lib.sas_reserve_isects(self._h, int(n)))
+
+    def stats(self) -> dict:
+        s = L.Stats()
+        L.check(self._lib, self._h, self._lib.sas_get_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_}
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.sas_last_launch_count(self._h))
+
+    # -- parity-test access to intermediates ------------------------------------------------
+    def debug_intermediates(self) -> dict:
+        """Intermediates of the last render in the oracle's layout (numpy, host)."""
+        s = self.stats()
+        I, N = self.I, self.N
+        tw, th = s["tile_w"], s["tile_h"]
+        T = tw * th
+        M = min(s["n_isects"], 2**31 - 16)
+        rec = np.empty((I, N, 12), dtype=np.float32)
+        bins = np.empty((I, N, 2), dtype=np.uint32)
+        offs = np.empty(I * T + 1, dtype=np.int32)
+        gids = np.empty(M, dtype=np.int32)
+        for what, arr in ((L.SAS_DBG_RECORDS, rec), (L.SAS_DBG_BINS, bins), (L.SAS_DBG_TILE_OFFSETS, offs), (L.SAS_DBG_SORTED_GIDS, gids)):
+            L.check(self._lib, self._h, self._lib.sas_debug_fetch(self._h, what, arr.ctypes.data, arr.nbytes))
+        rect = np.stack([bins[..., 0] & 0xff, (bins[..., 0] >> 8) & 0xff, (bins[..., 0] >> 16) & 0xff, bins[..., 0] >> 24], axis=-1).astype(np.int32)
+        vis = bins[..., 0] != 0
+        tiles = ((rect[..., 2] - rect[..., 0]) * (rect[..., 3] - rect[..., 1])).astype(np.int32)
+        z = lambda a: np.where(vis[..., None] if a.ndim == 3 else vis, a, 0).astype(a.dtype)  # noqa: E731
+        two = np.float32(2.0)
+        conics = np.stack([rec[..., 2] * two, rec[..., 3], rec[..., 4] * two], axis=-1)
+        tile_bits = int(T).bit_length()
+        # rebuild gsplat's 64-bit keys / flattened ids from the bucket structure
+        counts = np.diff(offs.astype(np.int64))
+        bucket = np.repeat(np.arange(I * T, dtype=np.int64), counts)[:M]
+        img, tile = bucket // T, bucket % T
+        flat = (img * N + gids.astype(np.int64))
+        depth_bits = bins.reshape(-1, 2)[flat, 1].astype(np.int64)
+        isect_ids = (img << (32 + tile_bits)) | (tile << 32) | depth_bits
+        return dict(
+            radii=z(rec[..., 6:8]).astype(np.int32), means2d=z(rec[..., 0:2]), depths=z(rec[..., 11]), conics=z(conics),
+            colors=z(rec[..., 8:11]), opacities=z(rec[..., 5]), tiles_per_gauss=z(tiles), tile_rect=z(rect), visible=vis,
+            isect_ids=isect_ids, flatten_ids=flat.astype(np.int32), isect_offsets=offs[:-1].reshape(I, th, tw).copy(),
+            M=M, tile_bits=tile_bits, stats=s,
+        )

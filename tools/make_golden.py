@@ -1,0 +1,248 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the reference itself (run in the build container only).
+
+`/root/reference` is Python over third-party packages that are not installed
+(viser, pydrake, urchin, open3d, trimesh, nerfstudio, gsplat).  The pieces of
+the hot path that ARE the reference's own arithmetic are executed here,
+unmodified, by importing the reference's files with stub modules in
+`sys.modules` for the absent third-party imports:
+
+* compute_cov.npz   - sim_a_splat/ellipsoids/covariance_utils.py (pure torch; runs as is)
+* sh2rgb.npz        - `C0` and `SH2RGB` lifted by `ast` from ns_utils/nerfstudio_utils.py:43-47
+                      (the module itself imports nerfstudio at the top)
+* draw_handler.npz  - `SplatHandler._load_saved_masks`, `.draw_handler`,
+                      `.get_attached_frame` from splat/splat_handler.py, bound to a bare
+                      object; `viser.transforms` is replaced by
+                      sim_a_splat_b200.transforms (checked against scipy in tests)
+* assets.npz        - the real masks (bit-packed), ICP matrices, intrinsics, a few
+                      training camera poses, dataparser transforms and a subsample of
+                      the robot surface points, so the GPU box (which has no
+                      /root/reference) can build scenes with the real N / mask structure.
+
+Nothing under tests/, bench.py or smoke() reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference")
+OUT = REPO / "tests" / "golden"
+sys.path.insert(0, str(REPO))
+
+
+def _load_by_path(name: str, path: Path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_compute_cov():
+    cu = _load_by_path("ref_covariance_utils", REF / "sim_a_splat/ellipsoids/covariance_utils.py")
+    g = torch.Generator().manual_seed(7)
+    quats = torch.randn(512, 4, generator=g)
+    quats[:64] *= 3.7  # un-normalised, as stored by splatfacto
+    quats[64:72] = torch.tensor([1.0, 0.0, 0.0, 0.0]) + 1e-4 * torch.randn(8, 4, generator=g)  # Taylor branch
+    quats[72:80, 0] = -quats[72:80, 0].abs()  # cos_theta < eps branch (covariance_utils.py:42-49)
+    scales = torch.exp(torch.randn(512, 3, generator=g) * 0.6 + np.log(0.008))
+    covs = cu.compute_cov(quats, scales)
+    covs_inv = cu.compute_cov(quats, 1.0 / scales)
+    rot = cu.quaternion_to_rotation_matrix(quats)
+    np.savez_compressed(OUT / "compute_cov.npz", quats=quats.numpy(), scales=scales.numpy(), covs=covs.numpy(),
+                        covs_inv=covs_inv.numpy(), rot=rot.numpy())
+    print("compute_cov.npz", covs.shape)
+
+
+def make_sh2rgb():
+    src = (REF / "sim_a_splat/ns_utils/nerfstudio_utils.py").read_text()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "C0")
+            or (isinstance(n, ast.FunctionDef) and n.name == "SH2RGB")]
+    ns: dict = {}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "nerfstudio_utils.py", "exec"), ns)
+    g = torch.Generator().manual_seed(11)
+    dc = torch.randn(256, 3, generator=g) * 1.5
+    np.savez_compressed(OUT / "sh2rgb.npz", C0=np.float64(ns["C0"]), dc=dc.numpy(), rgb=ns["SH2RGB"](dc).numpy())
+    print("sh2rgb.npz C0 =", ns["C0"])
+
+
+class _Handle:
+    def __init__(self):
+        self.wxyz = None
+        self.position = None
+
+
+class _Quat:
+    def __init__(self, w):
+        self._w = np.asarray(w, dtype=np.float64)
+
+    def wxyz(self):
+        return self._w
+
+
+class _Rot:
+    def ToQuaternion(self):
+        return _Quat([1.0, 0.0, 0.0, 0.0])
+
+
+class _Weld:
+    def __init__(self, t):
+        self._t = np.asarray(t, dtype=np.float64)
+
+    def translation(self):
+        return self._t
+
+    def rotation(self):
+        return _Rot()
+
+
+def _import_reference_splat_handler():
+    import sim_a_splat_b200.transforms as mytf
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    viser = stub("viser", ViserServer=object)
+    viser.transforms = mytf
+    sys.modules["viser.transforms"] = mytf
+    stub("drake", lcmt_viewer_draw=object, lcmt_viewer_load_robot=object)
+    stub("urchin", URDF=object)
+    stub("open3d")
+    stub("trimesh")
+    stub("pydrake")
+    stub("pydrake.all", RigidTransform=lambda: _Weld([0.0, 0.0, 0.0]))
+    stub("sim_a_splat")
+    stub("sim_a_splat.splat")
+    stub("sim_a_splat.splat.splat_utils", GSplatLoader=object)
+    stub("sim_a_splat.messaging")
+    stub("sim_a_splat.messaging.link", Link=object)
+    return _load_by_path("ref_splat_handler", REF / "sim_a_splat/splat/splat_handler.py")
+
+
+def make_draw_handler():
+    import sim_a_splat_b200.transforms as mytf
+
+    sh = _import_reference_splat_handler()
+    rng = np.random.default_rng(2024)
+    out = {}
+    mask_dirs = {
+        "xarm6-1": REF / "assets/robots-scene-v2/masks/xarm6-1",
+        "xarm6-2": REF / "assets/robots-scene-v2/masks/xarm6-2",
+        "xarm6-robot2": REF / "assets/robots-scene-v2/masks/xarm6-robot2",
+        "divar113vhw": REF / "assets/divar113vhw/masks/divar113vhw",
+    }
+    cases = []
+    for name, d in mask_dirs.items():
+        h = object.__new__(sh.SplatHandler)
+        h.masks_dir = str(d)
+        h._load_saved_masks()  # reference code: ICP factorisation + asserts
+        out[f"{name}/icp"] = np.load(d / "icp_transformation.npy")
+        out[f"{name}/scale_factor"] = np.float64(h.scale_factor)
+        out[f"{name}/Ri"] = np.asarray(h.Ri)
+        out[f"{name}/ti"] = np.asarray(h.ti)
+        L = len(h.link_masks_dict_saved)
+        nb = L + 1  # one more robot body than masks, like the xarm push gripper
+        for case in range(3):
+            weld = rng.uniform(-0.2, 0.2, size=3) if case else np.zeros(3)
+            h.sim_robot_weld_frame_transform = _Weld(weld)
+            h.rbt_idx, h.blk_idx = 3, 2
+            fk = [mytf.SE3.from_rotation_and_translation(mytf.SO3.exp(rng.uniform(-2, 2, 3)), rng.uniform(-0.5, 0.5, 3))
+                  for _ in range(nb)]
+            h.fk_tf = fk
+            h.mesh_frame_handles = [_Handle() for _ in range(nb)]
+            h.splat_links_handler = [_Handle() for _ in range(L)]
+            h.task_mesh_frame_handle = _Handle()
+            # message: T-block first (robot_num 2), then robot bodies (robot_num 3), one foreign body
+            B = nb + 2
+            msg = types.SimpleNamespace()
+            msg.num_links = B
+            msg.robot_num = [2] + [3] * nb + [7]
+            msg.link_name = ["plant::tblock_paper::tblock_paper"] + [f"plant::robot::link{i}" for i in range(nb)] + ["plant::other::x"]
+            q = rng.normal(size=(B, 4)) * rng.uniform(0.5, 2.0, size=(B, 1))  # deliberately un-normalised
+            p = rng.uniform(-0.6, 0.6, size=(B, 3))
+            msg.quaternion = [q[i] for i in range(B)]
+            msg.position = [p[i] for i in range(B)]
+            h.draw_handler(msg)  # reference code
+            nsplat = min(L, 7)  # `local_idx < 7` (splat_handler.py:282)
+            key = f"{name}/case{case}"
+            out[f"{key}/weld"] = weld
+            out[f"{key}/robot_num"] = np.asarray(msg.robot_num)
+            out[f"{key}/quaternion"] = q
+            out[f"{key}/position"] = p
+            out[f"{key}/fk_wxyz_xyz"] = np.stack([f.wxyz_xyz for f in fk])
+            out[f"{key}/splat_wxyz"] = np.stack([h.splat_links_handler[i].wxyz for i in range(nsplat)])
+            out[f"{key}/splat_position"] = np.stack([h.splat_links_handler[i].position for i in range(nsplat)])
+            out[f"{key}/mesh_wxyz"] = np.stack([m.wxyz for m in h.mesh_frame_handles])
+            out[f"{key}/mesh_position"] = np.stack([m.position for m in h.mesh_frame_handles])
+            out[f"{key}/task_wxyz"] = np.asarray(h.task_mesh_frame_handle.wxyz)
+            out[f"{key}/task_position"] = np.asarray(h.task_mesh_frame_handle.position)
+            local = mytf.SE3(np.concatenate(([1.0, 0, 0, 0], [-0.1, 0.0, 0.033])))  # tests/test_splat_wrapper.py:92-98
+            aw, ap = h.get_attached_frame("robot::link3", local, msg)  # reference code
+            out[f"{key}/attached_wxyz"] = np.asarray(aw)
+            out[f"{key}/attached_position"] = np.asarray(ap)
+            cases.append(key)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(OUT / "draw_handler.npz", **out)
+    print("draw_handler.npz", len(cases), "cases")
+
+
+def _read_pcd_xyz(path: Path) -> np.ndarray:
+    raw = path.read_bytes()
+    head_end = raw.index(b"DATA binary\n") + len(b"DATA binary\n")
+    header = raw[:head_end].decode()
+    n = int([ln for ln in header.splitlines() if ln.startswith("POINTS")][0].split()[1])
+    arr = np.frombuffer(raw[head_end:head_end + n * 24], dtype=np.float32).reshape(n, 6)
+    return arr[:, :3].copy()
+
+
+def make_assets():
+    out = {}
+    for scene, obj in (("robots-scene-v2", "xarm6-1"), ("divar113vhw", "divar113vhw")):
+        d = REF / "assets" / scene / "masks" / obj
+        masks = np.load(d / "link_masks_global_dict.npy", allow_pickle=True).item()
+        L = len(masks)
+        stack = np.stack([masks[f"link{i}"] for i in range(L)])
+        out[f"{scene}/N"] = np.int64(stack.shape[1])
+        out[f"{scene}/masks_packed"] = np.packbits(stack, axis=1)
+        out[f"{scene}/icp"] = np.load(d / "icp_transformation.npy")
+        jc = d / "joint_config.npy"
+        out[f"{scene}/joint_config"] = np.load(jc) if jc.exists() else np.zeros(0)
+        pts = _read_pcd_xyz(d / "point_cloud.pcd")
+        sel = np.random.default_rng(5).choice(pts.shape[0], size=8192, replace=False)
+        out[f"{scene}/surface_points"] = pts[np.sort(sel)]
+        tj = json.loads((REF / "assets" / scene / "transforms.json").read_text())
+        out[f"{scene}/intrinsics"] = np.array([tj["w"], tj["h"], tj["fl_x"], tj["fl_y"], tj["cx"], tj["cy"]], dtype=np.float64)
+        frames = tj["frames"][:: max(1, len(tj["frames"]) // 32)][:32]
+        out[f"{scene}/train_c2w"] = np.stack([np.asarray(f["transform_matrix"], dtype=np.float64) for f in frames])
+        sp = sorted((REF / "assets" / scene / "splatfacto").glob("*/dataparser_transforms.json"))[0]
+        dp = json.loads(sp.read_text())
+        out[f"{scene}/dataparser_transform"] = np.asarray(dp["transform"], dtype=np.float64)
+        out[f"{scene}/dataparser_scale"] = np.float64(dp["scale"])
+    # camera dict every reference script uses (tests/test_splat_wrapper.py:77-101)
+    out["script_camera0_wxyz_xyz"] = np.array([-0.41946813, 0.89955231, -0.11045113, 0.05150421, -0.15, -0.3, -0.05])
+    out["script_camera1_wxyz_xyz"] = np.array([1.0, 0, 0, 0, -0.1, 0, 0.033])
+    out["script_render_size"] = np.array([240, 320])
+    np.savez_compressed(OUT / "assets.npz", **out)
+    print("assets.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim > 0})
+
+
+if __name__ == "__main__":
+    OUT.mkdir(parents=True, exist_ok=True)
+    make_compute_cov()
+    make_sh2rgb()
+    make_draw_handler()
+    make_assets()
