@@ -98,6 +98,8 @@ typedef struct {
     int64_t n_isects;       /* M of the last render                                    */
     int64_t n_visible;      /* (image,gaussian) pairs with radii > 0                   */
     int64_t max_tile_list;  /* longest (image,tile) list                               */
+    int64_t n_staged;       /* Gaussian records the compositor staged into shared memory
+                               (sum over tiles, after early termination)               */
     int32_t overflow;       /* 1 if M exceeded max_isects (frame is incomplete)        */
     int32_t n_images, n_gaussians, width, height, tile_w, tile_h;
 } sas_stats;
@@ -139,6 +141,13 @@ int sas_get_stats(sas_renderer *r, sas_stats *out);
 #define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of per-(image,tile) counts          */
 #define SAS_DBG_SORTED_GIDS 4  /* [M] i32 Gaussian index per intersection, (image,tile,depth,gid) order */
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
+
+/* Per-stage device timing (CUDA events on the caller's stream around each stage of sas_render).
+ * Stages: 0 project, 1 scan, 2 emit, 3 bucket sort, 4 composite, 5 nerfstudio post.
+ * sas_get_stage_ms synchronises and returns the last render's stage durations in ms. */
+#define SAS_N_STAGES 6
+int sas_set_stage_timing(sas_renderer *r, int enable);
+int sas_get_stage_ms(sas_renderer *r, float *ms_out /*[SAS_N_STAGES]*/);
 
 /* Number of kernels the last sas_render enqueued (for bench.py's gpu_launches). */
 int sas_last_launch_count(const sas_renderer *r);

@@ -89,7 +89,7 @@ def camera_origin(viewmats: np.ndarray) -> np.ndarray:
 
 
 def render(scene: dict, viewmats, Ks, W: int, H: int, link_poses=None, env_of_image=None,
-           bg=(0.0, 0.0, 0.0), stages: int = 3) -> OracleFrame:
+           bg=(0.0, 0.0, 0.0), stages: int = 3, keep=None) -> OracleFrame:
     """scene: dict(means[N,3], quats[N,4] wxyz, scales[N,3] linear, opacities[N] linear,
     sh[N,K,3], link_id[N] int32 (-1 background), L).  link_poses [E,L,12] fp32."""
     lib = _lib()
@@ -124,8 +124,8 @@ def render(scene: dict, viewmats, Ks, W: int, H: int, link_poses=None, env_of_im
     M = int(f.M)
     th, tw = f.tile_h, f.tile_w
 
-    def arr(ptr, shape, dt):
-        if not ptr:
+    def arr(ptr, shape, dt, name=None):
+        if not ptr or (keep is not None and name not in keep):
             return None
         n = int(np.prod(shape))
         if n == 0:
@@ -136,15 +136,15 @@ def render(scene: dict, viewmats, Ks, W: int, H: int, link_poses=None, env_of_im
     out = OracleFrame(
         I=I, N=N, W=W, H=H, tile_w=tw, tile_h=th, tile_bits=f.tile_bits, image_bits=f.image_bits, M=M,
         pairs_evaluated=int(f.pairs_evaluated), campos=campos,
-        radii=arr(f.radii, (I, N, 2), np.int32), means2d=arr(f.means2d, (I, N, 2), np.float32),
-        depths=arr(f.depths, (I, N), np.float32), conics=arr(f.conics, (I, N, 3), np.float32),
-        colors=arr(f.colors, (I, N, 3), np.float32), tiles_per_gauss=arr(f.tiles_per_gauss, (I, N), np.int32),
-        tile_rect=arr(f.tile_rect, (I, N, 4), np.int32),
-        isect_ids=arr(f.isect_ids, (M,), np.int64), flatten_ids=arr(f.flatten_ids, (M,), np.int32),
-        isect_offsets=arr(f.isect_offsets, (I, th, tw), np.int32),
-        rgb=arr(f.rgb, (I, H, W, 3), np.float32), depth=arr(f.depth, (I, H, W), np.float32),
-        alpha=arr(f.alpha, (I, H, W), np.float32), n_contrib=arr(f.n_contrib, (I, H, W), np.int32),
-        last_idx=arr(f.last_idx, (I, H, W), np.int32),
+        radii=arr(f.radii, (I, N, 2), np.int32, "radii"), means2d=arr(f.means2d, (I, N, 2), np.float32, "means2d"),
+        depths=arr(f.depths, (I, N), np.float32, "depths"), conics=arr(f.conics, (I, N, 3), np.float32, "conics"),
+        colors=arr(f.colors, (I, N, 3), np.float32, "colors"), tiles_per_gauss=arr(f.tiles_per_gauss, (I, N), np.int32, "tiles_per_gauss"),
+        tile_rect=arr(f.tile_rect, (I, N, 4), np.int32, "tile_rect"),
+        isect_ids=arr(f.isect_ids, (M,), np.int64, "isect_ids"), flatten_ids=arr(f.flatten_ids, (M,), np.int32, "flatten_ids"),
+        isect_offsets=arr(f.isect_offsets, (I, th, tw), np.int32, "isect_offsets"),
+        rgb=arr(f.rgb, (I, H, W, 3), np.float32, "rgb"), depth=arr(f.depth, (I, H, W), np.float32, "depth"),
+        alpha=arr(f.alpha, (I, H, W), np.float32, "alpha"), n_contrib=arr(f.n_contrib, (I, H, W), np.int32, "n_contrib"),
+        last_idx=arr(f.last_idx, (I, H, W), np.int32, "last_idx"),
     )
     lib.orc_frame_free(fp)
     return out

@@ -21,7 +21,7 @@ SAS_DBG_SORTED_GIDS = 4
 
 EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
-    "sas_get_stats", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
+    "sas_get_stats", "sas_set_stage_timing", "sas_get_stage_ms", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
 ]
 
 
@@ -43,7 +43,7 @@ class Outputs(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("n_isects", C.c_int64), ("n_visible", C.c_int64), ("max_tile_list", C.c_int64), ("overflow", C.c_int32),
+    _fields_ = [("n_isects", C.c_int64), ("n_visible", C.c_int64), ("max_tile_list", C.c_int64), ("n_staged", C.c_int64), ("overflow", C.c_int32),
                 ("n_images", C.c_int32), ("n_gaussians", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
 
@@ -86,6 +86,10 @@ def load(build_if_missing: bool = True):
     lib.sas_reserve_isects.restype = C.c_int
     lib.sas_get_stats.argtypes = [P, C.POINTER(Stats)]
     lib.sas_get_stats.restype = C.c_int
+    lib.sas_set_stage_timing.argtypes = [P, C.c_int]
+    lib.sas_set_stage_timing.restype = C.c_int
+    lib.sas_get_stage_ms.argtypes = [P, C.POINTER(C.c_float)]
+    lib.sas_get_stage_ms.restype = C.c_int
     lib.sas_debug_fetch.argtypes = [P, C.c_int, P, C.c_size_t]
     lib.sas_debug_fetch.restype = C.c_int
     lib.sas_last_launch_count.argtypes = [P]

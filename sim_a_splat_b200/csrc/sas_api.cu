@@ -44,6 +44,8 @@ struct sas_renderer {
     SasCounters *counters = nullptr;
     bool rendered = false;
     int last_launches = 0;
+    bool stage_timing = false;
+    cudaEvent_t stage_ev[SAS_N_STAGES + 1] = {};
 };
 
 namespace {
@@ -186,6 +188,8 @@ void sas_destroy(sas_renderer *r) {
     cudaFree(r->link_poses); cudaFree(r->cams); cudaFree(r->counters);
     if (r->cams_host) cudaFreeHost(r->cams_host);
     if (r->cams_copied) cudaEventDestroy(r->cams_copied);
+    for (cudaEvent_t ev : r->stage_ev)
+        if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->tile_count, &r->tile_cursor, &r->tile_offset, &r->block_sums, &r->pairs, &r->pairs_alt,
                       &r->sorted_gid, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc};
     for (DevBuf *b : bufs) free_buf(*b);
@@ -298,26 +302,36 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     SAS_CUDA(r, cudaMemsetAsync(r->tile_cursor.p, 0, IT * 4, st));
     SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters), st));
 
+#define SAS_STAGE(i) do { if (r->stage_timing) SAS_CUDA(r, cudaEventRecord(r->stage_ev[i], st)); } while (0)
+    SAS_STAGE(0);
     SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, N, r->sh_degree,
                                    r->L > 0 ? r->link_poses : nullptr, r->L, r->cams, I, W, H, tw, th, (SasRecord *)r->rec.p,
                                    (uint2 *)r->bins.p, (unsigned *)r->tile_count.p, r->counters, st));
     launches += 1;
+    SAS_STAGE(1);
     SAS_CUDA(r, sas_launch_scan((const unsigned *)r->tile_count.p, (int)IT, (int *)r->tile_offset.p, (unsigned *)r->block_sums.p,
                                 r->counters, r->max_isects, st, &launches));
+    SAS_STAGE(2);
     SAS_CUDA(r, sas_launch_emit((const uint2 *)r->bins.p, N, I, tw, th, (const int *)r->tile_offset.p, (unsigned *)r->tile_cursor.p,
                                 (uint2 *)r->pairs.p, r->max_isects, st));
     launches += 1;
+    SAS_STAGE(3);
     SAS_CUDA(r, sas_launch_tile_sort((uint2 *)r->pairs.p, (uint2 *)r->pairs_alt.p, (const int *)r->tile_offset.p, (int)IT,
                                      (int *)r->sorted_gid.p, r->max_isects, st, &launches));
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
+    SAS_STAGE(4);
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
     SAS_CUDA(r, sas_launch_composite((const SasRecord *)r->rec.p, (const int *)r->sorted_gid.p, (const int *)r->tile_offset.p, N, I, W,
-                                     H, tw, th, b0, b1, b2, d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, st));
+                                     H, tw, th, b0, b1, b2, d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, r->counters,
+                                     st));
     launches += 1;
+    SAS_STAGE(5);
     if (ns) {
         SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, I, W, H, out->background[0], out->background[1],
                                        out->background[2], (unsigned *)r->img_max.p, st, &launches));
     }
+    SAS_STAGE(6);
+#undef SAS_STAGE
     r->last_launches = launches;
     r->rendered = true;
     if (host_out) {
@@ -331,6 +345,25 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     return SAS_OK;
 }
 
+int sas_set_stage_timing(sas_renderer *r, int enable) {
+    if (!r) return SAS_EINVAL;
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    if (enable)
+        for (cudaEvent_t &ev : r->stage_ev)
+            if (!ev) SAS_CUDA(r, cudaEventCreate(&ev));
+    r->stage_timing = enable != 0;
+    return SAS_OK;
+}
+
+int sas_get_stage_ms(sas_renderer *r, float *ms_out) {
+    if (!r || !ms_out) return SAS_EINVAL;
+    if (!r->stage_timing || !r->rendered) return fail(r, SAS_ESTATE, "sas_get_stage_ms: stage timing is off or nothing rendered");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaEventSynchronize(r->stage_ev[SAS_N_STAGES]));
+    for (int i = 0; i < SAS_N_STAGES; i++) SAS_CUDA(r, cudaEventElapsedTime(ms_out + i, r->stage_ev[i], r->stage_ev[i + 1]));
+    return SAS_OK;
+}
+
 int sas_get_stats(sas_renderer *r, sas_stats *out) {
     if (!r || !out) return SAS_EINVAL;
     SAS_CUDA(r, cudaSetDevice(r->device));
@@ -339,6 +372,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
     SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out->n_isects = (int64_t)c.n_isects;
     out->n_visible = (int64_t)c.n_visible;
+    out->n_staged = (int64_t)c.n_staged;
     out->max_tile_list = (int64_t)c.max_tile_list;
     out->overflow = (int32_t)c.overflow;
     out->n_images = r->I; out->n_gaussians = r->N; out->width = r->W; out->height = r->H;

@@ -75,6 +75,7 @@ __device__ __forceinline__ void sas_cp_async_wait() {
 struct SasCounters {
     unsigned long long n_isects;
     unsigned long long n_visible;
+    unsigned long long n_staged;
     unsigned int max_tile_list;
     unsigned int overflow;
 };
@@ -92,6 +93,7 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *tile
                                  long long max_isects, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *sorted_gid, const int *tile_offset, int N, int I, int W,
                                  int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, float *rgb, float *depth,
-                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, cudaStream_t st);
+                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, SasCounters *counters,
+                                 cudaStream_t st);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
                                                        const int *__restrict__ tile_offset, int N, int W, int H, int tile_w, int tile_h,
                                                        float bg0, float bg1, float bg2, float *__restrict__ out_rgb,
                                                        float *__restrict__ out_depth, float *__restrict__ out_alpha,
-                                                       uint8_t *__restrict__ out_u8, int *__restrict__ out_nc, long long max_isects) {
+                                                       uint8_t *__restrict__ out_u8, int *__restrict__ out_nc, long long max_isects,
+                                                       SasCounters *counters) {
     __shared__ SasRecord stage[2][CB];
 
     const int tile = blockIdx.x, im = blockIdx.y;
@@ -72,9 +73,11 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
     sas_cp_async_commit();
     if (CB + tid < n) gid_next = __ldg(gids + CB + tid);
 
+    int staged = 0;
     for (int b = 0; b < nb; b++) {
         sas_cp_async_wait<0>();
         if (__syncthreads_count(done) == CB) break;  // also publishes batch b to the CTA
+        staged += min(CB, n - b * CB);
         const int buf = b & 1;
         {  // batch b+1 -> other buffer; id of batch b+2 -> register
             const int e1 = (b + 1) * CB + tid;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
         }
     }
     sas_cp_async_wait<0>();
+    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged);
 
     if (inside) {
         const size_t pi = ((size_t)im * H + py) * W + px;
@@ -174,10 +178,11 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *sorted_gid, const int *tile_offset, int N, int I, int W,
                                  int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, float *rgb, float *depth,
-                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, cudaStream_t st) {
+                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, SasCounters *counters,
+                                 cudaStream_t st) {
     dim3 grid(tile_w * tile_h, I);
     composite_kernel<<<grid, CB, 0, st>>>(rec, sorted_gid, tile_offset, N, W, H, tile_w, tile_h, bg0, bg1, bg2, rgb, depth, alpha,
-                                          rgb_u8, n_contrib, max_isects);
+                                          rgb_u8, n_contrib, max_isects, counters);
     return cudaGetLastError();
 }
 

@@ -153,6 +153,16 @@ class SplatRenderer:
         L.check(self._lib, self._h, self._lib.sas_get_stats(self._h, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in L.Stats._fields_}
 
+    STAGES = ("project", "scan", "emit", "sort", "composite", "post")
+
+    def set_stage_timing(self, enable: bool) -> None:
+        L.check(self._lib, self._h, self._lib.sas_set_stage_timing(self._h, 1 if enable else 0))
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * len(self.STAGES))()
+        L.check(self._lib, self._h, self._lib.sas_get_stage_ms(self._h, ms))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
     def last_launch_count(self) -> int:
         return int(self._lib.sas_last_launch_count(self._h))
 
