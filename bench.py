@@ -90,17 +90,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(st: dict, N: int, I: int, K_sh: int, out_bytes_per_px: int) -> dict:
+def algorithmic_bytes(st: dict, N: int, K_sh: int, out_bytes_per_px: int) -> dict:
     """ALGORITHMIC bytes per launch (DESIGN.md 'Kernels and rooflines'): the bytes each stage must move if
-    every operand were read / written exactly once per image; counted from the measured N_vis, M, staged."""
-    n_vis, M, staged = st["n_visible"], st["n_isects"], st["n_staged"]
-    T, P = st["tile_w"] * st["tile_h"] * I, st["width"] * st["height"] * I
+    every operand of the work it actually does were read / written exactly once; counted from the
+    measured counters.  Background rows are views (shared by all images with that camera), link rows
+    are images -- the sharing lowers the work, and only the work done is counted."""
+    I, C, nbg = st["n_images"], st["n_views"], st["n_background"]
+    n_rows_g = C * nbg + I * (N - nbg)          # (row, gaussian) projections
+    T = st["tile_w"] * st["tile_h"]
+    P = st["width"] * st["height"] * I
+    M, M_src, n_vis, staged = st["n_isects"], st["n_isects_src"], st["n_visible_src"], st["n_staged"]
     return {
-        "project": I * N * (48 + 12 * K_sh) + I * N * 8 + n_vis * 48,
-        "scan": T * 8,
-        "emit": I * N * 8 + M * 8,
-        "sort": M * 12,
-        "composite": staged * 52 + T * 8 + P * out_bytes_per_px,
+        "project": n_rows_g * (48 + 12 * K_sh) + n_rows_g * 8 + n_vis * 48,
+        "scan": ((C + I) * T + I * T) * 8,
+        "emit": n_rows_g * 8 + M_src * 8,
+        "sort": M_src * 16 + M * 12,                 # bucket sort (8 B in, 8 B out) + merge (8 B in, 4 B out)
+        "composite": staged * 52 + I * T * 8 + P * out_bytes_per_px,
     }
 
 
@@ -205,7 +210,7 @@ def run_ours(args):
     if rank == 0:
         frames = I * world * args.steps
         K_sh = (SH_DEG + 1) ** 2
-        ab = algorithmic_bytes(st, sc.N, I, K_sh, 20)
+        ab = algorithmic_bytes(st, sc.N, K_sh, 20)
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
@@ -235,7 +240,7 @@ def run_ours(args):
                               "peak": hbm, "unit": "GB/s", "frac": round(sum(ab.values()) / (sum(stage.values()) * 1e-3) / 1e9 / hbm, 4)},
             "stages": stages,
             "fp32": {"staged_gaussians_per_step": st["n_staged"], "pixel_gaussian_pairs_per_s": round(st["n_staged"] * 256 / (stage["composite"] * 1e-3), 1)},
-            "counts": {"n_visible": st["n_visible"], "n_isects": st["n_isects"], "max_tile_list": st["max_tile_list"]},
+            "counts": {k: st[k] for k in ("n_views", "n_images", "n_background", "n_visible_src", "n_isects_src", "n_isects", "max_tile_list")},
             "clocks": clocks.summary(),
         }
         if gather:

@@ -94,14 +94,19 @@ typedef struct {
     int32_t *n_contrib;     /* [I,H,W]   Gaussians accumulated per pixel (diagnostic)  */
 } sas_outputs;
 
+/* Images that share a camera (bit-identical viewmat and K) share a VIEW: the background
+ * (link_id < 0) is projected, binned and depth-sorted once per view, the link Gaussians once
+ * per image, and the two sorted lists of every (image,tile) are merged.  "src" counts below
+ * are the work actually done; n_isects is gsplat's per-image intersection count. */
 typedef struct {
-    int64_t n_isects;       /* M of the last render                                    */
-    int64_t n_visible;      /* (image,gaussian) pairs with radii > 0                   */
-    int64_t max_tile_list;  /* longest (image,tile) list                               */
+    int64_t n_isects;       /* M of the last render: merged (image,tile,gaussian) intersections */
+    int64_t n_isects_src;   /* bucket entries emitted and sorted (background per view + links per image) */
+    int64_t n_visible_src;  /* (row,gaussian) projections with radii > 0 (rows = views, then images) */
+    int64_t max_tile_list;  /* longest merged (image,tile) list                        */
     int64_t n_staged;       /* Gaussian records the compositor staged into shared memory
                                (sum over tiles, after early termination)               */
-    int32_t overflow;       /* 1 if M exceeded max_isects (frame is incomplete)        */
-    int32_t n_images, n_gaussians, width, height, tile_w, tile_h;
+    int32_t overflow;       /* != 0 if an intersection count exceeded max_isects (frame is incomplete) */
+    int32_t n_images, n_views, n_gaussians, n_background, width, height, tile_w, tile_h;
 } sas_stats;
 
 /* Replaces: GSplatLoader -> SplatHandler._load_saved_splats + _add_robot_segmented_splats +
@@ -136,10 +141,12 @@ int sas_reserve_isects(sas_renderer *r, long long max_isects);
 int sas_get_stats(sas_renderer *r, sas_stats *out);
 
 /* Intermediates of the last render, for parity tests (synchronises). */
-#define SAS_DBG_RECORDS 1   /* [I,N,12] f32: m2x,m2y,0.5*conic_a,conic_b, 0.5*conic_c,opacity,radius_x,radius_y, r,g,b,depth */
-#define SAS_DBG_BINS 2      /* [I,N,2] u32: (x0 | y0<<8 | x1<<16 | y1<<24), bits(depth); tile rect, exclusive max */
-#define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of per-(image,tile) counts          */
-#define SAS_DBG_SORTED_GIDS 4  /* [M] i32 Gaussian index per intersection, (image,tile,depth,gid) order */
+#define SAS_DBG_RECORDS 1   /* [C*n_bg + I*(N-n_bg), 12] f32: per view the background records, then per image the link
+                               records: m2x,m2y,0.5*conic_a,conic_b, 0.5*conic_c,opacity,radius_x,radius_y, r,g,b,depth */
+#define SAS_DBG_BINS 2      /* same rows, [.,2] u32: (x0 | y0<<8 | x1<<16 | y1<<24), bits(depth); tile rect, exclusive max */
+#define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of the merged per-(image,tile) counts = gsplat isect_offsets */
+#define SAS_DBG_SORTED_GIDS 4  /* [M] i32 canonical Gaussian index per intersection, (image,tile,depth,gid) order */
+#define SAS_DBG_VIEW_OF_IMAGE 5 /* [I] i32 */
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
 
 /* Per-stage device timing (CUDA events on the caller's stream around each stage of sas_render).

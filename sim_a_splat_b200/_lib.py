@@ -18,6 +18,7 @@ SAS_DBG_RECORDS = 1
 SAS_DBG_BINS = 2
 SAS_DBG_TILE_OFFSETS = 3
 SAS_DBG_SORTED_GIDS = 4
+SAS_DBG_VIEW_OF_IMAGE = 5
 
 EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
@@ -43,8 +44,9 @@ class Outputs(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("n_isects", C.c_int64), ("n_visible", C.c_int64), ("max_tile_list", C.c_int64), ("n_staged", C.c_int64), ("overflow", C.c_int32),
-                ("n_images", C.c_int32), ("n_gaussians", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+    _fields_ = [("n_isects", C.c_int64), ("n_isects_src", C.c_int64), ("n_visible_src", C.c_int64), ("max_tile_list", C.c_int64),
+                ("n_staged", C.c_int64), ("overflow", C.c_int32), ("n_images", C.c_int32), ("n_views", C.c_int32),
+                ("n_gaussians", C.c_int32), ("n_background", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
 
 

@@ -1,7 +1,7 @@
 // sas_api.cu -- C ABI of libsas_b200.so (see include/sas.h for the contract and the reference
-// interfaces each entry point replaces).  Host-side only: buffer management, camera packing,
-// kernel sequencing on the caller's stream.  No CPU fallback exists: without a usable CUDA
-// device every entry point fails with SAS_ECUDA.
+// interfaces each entry point replaces).  Host-side only: buffer management, camera packing and
+// view de-duplication, kernel sequencing on the caller's stream.  No CPU fallback exists:
+// without a usable CUDA device every entry point fails with SAS_ECUDA.
 #include "../../include/sas.h"
 #include "sas_common.cuh"
 
@@ -23,7 +23,7 @@ struct DevBuf {
 
 struct sas_renderer {
     int device = 0;
-    int N = 0, n_pad = 0, sh_degree = 0, L = 0;
+    int N = 0, n_bg = 0, n_dyn = 0, n_pad = 0, sh_degree = 0, L = 0;
     sas_config cfg{};
     std::string err;
     // scene (SoA)
@@ -32,13 +32,16 @@ struct sas_renderer {
     // per-call state
     float *link_poses = nullptr;
     int n_envs = 0;
-    SasCamera *cams = nullptr;
-    SasCamera *cams_host = nullptr;  // pinned staging
+    SasCamera *row_cams = nullptr;       // [C views | I images]
+    int *view_of_image = nullptr;        // [I]
+    unsigned char *stage_host = nullptr; // pinned staging: row cams + view_of_image
+    size_t stage_bytes = 0;
     cudaEvent_t cams_copied = nullptr;
-    int I = 0, W = 0, H = 0, tile_w = 0, tile_h = 0;
+    std::vector<int> h_view_of_image;
+    int I = 0, C = 0, W = 0, H = 0, tile_w = 0, tile_h = 0;
     bool cameras_set = false;
     // grow-only work buffers
-    DevBuf rec, bins, tile_count, tile_cursor, tile_offset, block_sums, pairs, pairs_alt, sorted_gid, img_max;
+    DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -60,7 +63,7 @@ int fail(sas_renderer *r, int code, const std::string &msg) {
         cudaError_t e_ = (call);                                                                           \
         if (e_ != cudaSuccess) {                                                                           \
             char buf_[512];                                                                                \
-            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            snprintf(buf_, sizeof(buf_), "%.300s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
             return fail((r), e_ == cudaErrorMemoryAllocation ? SAS_ENOMEM : SAS_ECUDA, buf_);              \
         }                                                                                                  \
     } while (0)
@@ -89,16 +92,37 @@ int ensure_isects(sas_renderer *r, long long m) {
     int rc;
     if ((rc = ensure(r, r->pairs, (size_t)m * sizeof(uint2)))) return rc;
     if ((rc = ensure(r, r->pairs_alt, (size_t)m * sizeof(uint2)))) return rc;
-    if ((rc = ensure(r, r->sorted_gid, (size_t)m * sizeof(int)))) return rc;
+    if ((rc = ensure(r, r->merged, (size_t)m * sizeof(int)))) return rc;
     r->max_isects = m;
     return SAS_OK;
+}
+
+void fill_camera(SasCamera &c, const float *vm, const float *K, int width, int height, int env) {
+    for (int k = 0; k < 12; k++) c.vm[k] = vm[k];
+    c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+    // camera origin -R^T t in fp64, rounded once (the oracle does the same on the same fp32 viewmat)
+    for (int a = 0; a < 3; a++) {
+        double s = 0.0;
+        for (int b = 0; b < 3; b++) s += (double)vm[4 * b + a] * (double)vm[4 * b + 3];
+        c.campos[a] = (float)(-s);
+    }
+    c.env = env;
+    // same fp32 operation sequence as oracle/splat_oracle.c:project_one (host code is built with
+    // -ffp-contract=off, SSE fp32: every operation individually rounded)
+    const volatile float Wf = (float)width, Hf = (float)height;
+    const volatile float tan_fovx = 0.5f * Wf / c.fx, tan_fovy = 0.5f * Hf / c.fy;
+    const volatile float ax = 0.3f * tan_fovx, ay = 0.3f * tan_fovy;
+    c.lim_x_pos = (Wf - c.cx) / c.fx + ax;
+    c.lim_x_neg = c.cx / c.fx + ax;
+    c.lim_y_pos = (Hf - c.cy) / c.fy + ay;
+    c.lim_y_neg = c.cy / c.fy + ay;
 }
 
 }  // namespace
 
 extern "C" {
 
-const char *sas_version(void) { return "sas_b200 0.1.0 (sm_100a)"; }
+const char *sas_version(void) { return "sas_b200 0.2.0 (sm_100a)"; }
 
 const char *sas_last_error(const sas_renderer *r) { return r ? r->err.c_str() : g_create_error.c_str(); }
 
@@ -110,8 +134,8 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     if (scene->n_gaussians <= 0 || scene->sh_degree < 0 || scene->sh_degree > 3 || scene->n_links < 0 || !scene->means ||
         !scene->quats || !scene->scales || !scene->opacities || !scene->sh)
         return fail(nullptr, SAS_EINVAL, "sas_create: bad scene descriptor");
-    if (cfg->max_width > 4080 || cfg->max_height > 4080 || cfg->max_images <= 0 || cfg->max_images > 65535)
-        return fail(nullptr, SAS_EINVAL, "sas_create: max_width/max_height must be <= 4080 and 0 < max_images <= 65535");
+    if (cfg->max_width > 4080 || cfg->max_height > 4080 || cfg->max_images <= 0 || cfg->max_images > 32767)
+        return fail(nullptr, SAS_EINVAL, "sas_create: max_width/max_height must be <= 4080 and 0 < max_images <= 32767");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
@@ -130,6 +154,7 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
 #define SAS_TRY(x) do { int rc_ = (x); if (rc_) return bail(rc_); } while (0)
 #define SAS_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { r->err = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? SAS_ENOMEM : SAS_ECUDA); } } while (0)
     SAS_CUDA_C(cudaSetDevice(device));
+    SAS_CUDA_C(sas_sort_init());
 
     // bring the scene to the host if needed, pack SoA, upload
     std::vector<float> h_means((size_t)N * 3), h_quats((size_t)N * 4), h_scales((size_t)N * 3), h_op(N), h_sh((size_t)N * K * 3);
@@ -140,9 +165,16 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(cudaMemcpy(h_scales.data(), scene->scales, h_scales.size() * 4, kind));
     SAS_CUDA_C(cudaMemcpy(h_op.data(), scene->opacities, h_op.size() * 4, kind));
     SAS_CUDA_C(cudaMemcpy(h_sh.data(), scene->sh, h_sh.size() * 4, kind));
-    if (scene->link_id) SAS_CUDA_C(cudaMemcpy(h_link.data(), scene->link_id, (size_t)N * 4, kind));
-    for (int g = 0; g < N; g++)
-        if (h_link[g] >= scene->n_links) { r->err = "sas_create: link_id out of range"; return bail(SAS_EINVAL); }
+    if (scene->link_id && scene->n_links > 0) SAS_CUDA_C(cudaMemcpy(h_link.data(), scene->link_id, (size_t)N * 4, kind));
+    // canonical order: all background Gaussians (link_id < 0) first, then the link copies
+    int n_bg = 0;
+    while (n_bg < N && h_link[n_bg] < 0) n_bg++;
+    for (int g = n_bg; g < N; g++)
+        if (h_link[g] < 0 || h_link[g] >= scene->n_links) {
+            r->err = "sas_create: scene is not in canonical order (background first, then links) or link_id out of range";
+            return bail(SAS_EINVAL);
+        }
+    r->n_bg = n_bg; r->n_dyn = N - n_bg;
 
     std::vector<float4> p_mean(N), p_quat(N), p_scale(N);
     std::vector<float> p_sh((size_t)K * 3 * r->n_pad, 0.0f);
@@ -167,8 +199,10 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
 
     const int maxE = cfg->max_envs > 0 ? cfg->max_envs : 1;
     if (r->L > 0) SAS_CUDA_C(cudaMalloc(&r->link_poses, sizeof(float) * 12 * (size_t)maxE * r->L));
-    SAS_CUDA_C(cudaMalloc(&r->cams, sizeof(SasCamera) * cfg->max_images));
-    SAS_CUDA_C(cudaMallocHost(&r->cams_host, sizeof(SasCamera) * cfg->max_images));
+    SAS_CUDA_C(cudaMalloc(&r->row_cams, sizeof(SasCamera) * 2 * cfg->max_images));
+    SAS_CUDA_C(cudaMalloc(&r->view_of_image, sizeof(int) * cfg->max_images));
+    r->stage_bytes = sizeof(SasCamera) * 2 * cfg->max_images + sizeof(int) * cfg->max_images;
+    SAS_CUDA_C(cudaMallocHost(&r->stage_host, r->stage_bytes));
     SAS_CUDA_C(cudaEventCreateWithFlags(&r->cams_copied, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters)));
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters)));
@@ -185,13 +219,13 @@ void sas_destroy(sas_renderer *r) {
     cudaSetDevice(r->device);
     cudaDeviceSynchronize();
     cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
-    cudaFree(r->link_poses); cudaFree(r->cams); cudaFree(r->counters);
-    if (r->cams_host) cudaFreeHost(r->cams_host);
+    cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters);
+    if (r->stage_host) cudaFreeHost(r->stage_host);
     if (r->cams_copied) cudaEventDestroy(r->cams_copied);
     for (cudaEvent_t ev : r->stage_ev)
         if (ev) cudaEventDestroy(ev);
-    DevBuf *bufs[] = {&r->rec, &r->bins, &r->tile_count, &r->tile_cursor, &r->tile_offset, &r->block_sums, &r->pairs, &r->pairs_alt,
-                      &r->sorted_gid, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc};
+    DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
+                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -222,51 +256,59 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     if (n_images > r->cfg.max_images) return fail(r, SAS_ECAPACITY, "sas_set_cameras: n_images exceeds max_images");
     if (width > r->cfg.max_width || height > r->cfg.max_height || width > 4080 || height > 4080)
         return fail(r, SAS_ECAPACITY, "sas_set_cameras: image size exceeds max_width/max_height");
+    const int maxE = r->cfg.max_envs > 0 ? r->cfg.max_envs : 1;
+    for (int i = 0; i < n_images; i++) {
+        const int env = env_of_image ? env_of_image[i] : 0;
+        if (env < 0 || (r->L > 0 && env >= maxE)) return fail(r, SAS_EINVAL, "sas_set_cameras: env_of_image out of range");
+    }
     SAS_CUDA(r, cudaSetDevice(r->device));
     SAS_CUDA(r, cudaEventSynchronize(r->cams_copied));  // previous staging copy finished
+
+    // Views: images with bit-identical (viewmat, K) share one view; the background is projected,
+    // binned and sorted once per view.  Byte-wise comparison against the views found so far
+    // (a handful in practice; the scan is bounded to keep this O(I)).
+    std::vector<int> view_first;  // image index that defined each view
+    r->h_view_of_image.assign(n_images, 0);
     for (int i = 0; i < n_images; i++) {
-        const float *vm = viewmats + 16 * (size_t)i;
-        const float *K = Ks + 9 * (size_t)i;
-        SasCamera &c = r->cams_host[i];
-        for (int k = 0; k < 12; k++) c.vm[k] = vm[k];
-        c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
-        // camera origin -R^T t in fp64, rounded once (the oracle does the same on the same fp32 viewmat)
-        for (int a = 0; a < 3; a++) {
-            double s = 0.0;
-            for (int b = 0; b < 3; b++) s += (double)vm[4 * b + a] * (double)vm[4 * b + 3];
-            c.campos[a] = (float)(-s);
+        int v = -1;
+        const size_t nv = view_first.size();
+        for (size_t k = nv > 64 ? nv - 64 : 0; k < nv; k++) {
+            const int j = view_first[k];
+            if (memcmp(viewmats + 16 * (size_t)i, viewmats + 16 * (size_t)j, 64) == 0 && memcmp(Ks + 9 * (size_t)i, Ks + 9 * (size_t)j, 36) == 0) {
+                v = (int)k;
+                break;
+            }
         }
-        const int env = env_of_image ? env_of_image[i] : 0;
-        if (env < 0 || (r->L > 0 && env >= (r->cfg.max_envs > 0 ? r->cfg.max_envs : 1)))
-            return fail(r, SAS_EINVAL, "sas_set_cameras: env_of_image out of range");
-        c.env = env;
-        {   // same fp32 operation sequence as oracle/splat_oracle.c:project_one (host code is built
-            // with -ffp-contract=off, SSE fp32: every operation individually rounded)
-            const volatile float Wf = (float)width, Hf = (float)height;
-            const volatile float tan_fovx = 0.5f * Wf / c.fx, tan_fovy = 0.5f * Hf / c.fy;
-            const volatile float ax = 0.3f * tan_fovx, ay = 0.3f * tan_fovy;
-            c.lim_x_pos = (Wf - c.cx) / c.fx + ax;
-            c.lim_x_neg = c.cx / c.fx + ax;
-            c.lim_y_pos = (Hf - c.cy) / c.fy + ay;
-            c.lim_y_neg = c.cy / c.fy + ay;
-        }
+        if (v < 0) { v = (int)view_first.size(); view_first.push_back(i); }
+        r->h_view_of_image[i] = v;
+    }
+    const int C = (int)view_first.size();
+    SasCamera *cams = reinterpret_cast<SasCamera *>(r->stage_host);
+    int *voi = reinterpret_cast<int *>(r->stage_host + sizeof(SasCamera) * (size_t)(C + n_images));
+    for (int v = 0; v < C; v++) fill_camera(cams[v], viewmats + 16 * (size_t)view_first[v], Ks + 9 * (size_t)view_first[v], width, height, 0);
+    for (int i = 0; i < n_images; i++) {
+        fill_camera(cams[C + i], viewmats + 16 * (size_t)i, Ks + 9 * (size_t)i, width, height, env_of_image ? env_of_image[i] : 0);
+        voi[i] = r->h_view_of_image[i];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    SAS_CUDA(r, cudaMemcpyAsync(r->cams, r->cams_host, sizeof(SasCamera) * n_images, cudaMemcpyHostToDevice, st));
+    SAS_CUDA(r, cudaMemcpyAsync(r->row_cams, cams, sizeof(SasCamera) * (size_t)(C + n_images), cudaMemcpyHostToDevice, st));
+    SAS_CUDA(r, cudaMemcpyAsync(r->view_of_image, voi, sizeof(int) * (size_t)n_images, cudaMemcpyHostToDevice, st));
     SAS_CUDA(r, cudaEventRecord(r->cams_copied, st));
-    r->I = n_images; r->W = width; r->H = height;
+    r->I = n_images; r->C = C; r->W = width; r->H = height;
     r->tile_w = (width + SAS_TILE - 1) / SAS_TILE;
     r->tile_h = (height + SAS_TILE - 1) / SAS_TILE;
     r->cameras_set = true;
     // size the grow-only work buffers for this shape
-    const size_t IN = (size_t)n_images * r->N, IT = (size_t)n_images * r->tile_w * r->tile_h;
+    const size_t T = (size_t)r->tile_w * r->tile_h;
+    const size_t n_rec = (size_t)C * r->n_bg + (size_t)n_images * r->n_dyn, RT = (size_t)(C + n_images) * T, IT = (size_t)n_images * T;
     int rc;
-    if ((rc = ensure(r, r->rec, IN * sizeof(SasRecord)))) return rc;
-    if ((rc = ensure(r, r->bins, IN * sizeof(uint2)))) return rc;
-    if ((rc = ensure(r, r->tile_count, IT * 4))) return rc;
-    if ((rc = ensure(r, r->tile_cursor, IT * 4))) return rc;
-    if ((rc = ensure(r, r->tile_offset, (IT + 1) * 4))) return rc;
-    if ((rc = ensure(r, r->block_sums, (IT / 1024 + 2) * 4))) return rc;
+    if ((rc = ensure(r, r->rec, n_rec * sizeof(SasRecord)))) return rc;
+    if ((rc = ensure(r, r->bins, n_rec * sizeof(uint2)))) return rc;
+    if ((rc = ensure(r, r->row_tile_count, RT * 4))) return rc;
+    if ((rc = ensure(r, r->row_tile_cursor, RT * 4))) return rc;
+    if ((rc = ensure(r, r->row_tile_offset, (RT + 1) * 4))) return rc;
+    if ((rc = ensure(r, r->img_tile_offset, (IT + 1) * 4))) return rc;
+    if ((rc = ensure(r, r->block_sums, (RT / 1024 + 2) * 4))) return rc;
     if ((rc = ensure(r, r->img_max, (size_t)n_images * 4))) return rc;
     return SAS_OK;
 }
@@ -274,11 +316,11 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
 int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     if (!r || !out) return SAS_EINVAL;
     if (!r->cameras_set) return fail(r, SAS_ESTATE, "sas_render: sas_set_cameras has not been called");
-    if (r->L > 0 && r->n_envs == 0) return fail(r, SAS_ESTATE, "sas_render: scene has links but sas_set_link_poses has not been called");
+    if (r->n_dyn > 0 && r->n_envs == 0) return fail(r, SAS_ESTATE, "sas_render: scene has links but sas_set_link_poses has not been called");
     SAS_CUDA(r, cudaSetDevice(r->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int I = r->I, W = r->W, H = r->H, tw = r->tile_w, th = r->tile_h, N = r->N;
-    const size_t IT = (size_t)I * tw * th, P = (size_t)I * W * H;
+    const int I = r->I, C = r->C, W = r->W, H = r->H, tw = r->tile_w, th = r->tile_h, T = tw * th;
+    const size_t RT = (size_t)(C + I) * T, IT = (size_t)I * T, P = (size_t)I * W * H;
     int launches = 0;
 
     float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
@@ -298,32 +340,46 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         if (!d_alpha) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
     }
 
-    SAS_CUDA(r, cudaMemsetAsync(r->tile_count.p, 0, IT * 4, st));
-    SAS_CUDA(r, cudaMemsetAsync(r->tile_cursor.p, 0, IT * 4, st));
+    SAS_CUDA(r, cudaMemsetAsync(r->row_tile_count.p, 0, RT * 4, st));
+    SAS_CUDA(r, cudaMemsetAsync(r->row_tile_cursor.p, 0, RT * 4, st));
     SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters), st));
+
+    SasRecord *rec = (SasRecord *)r->rec.p;
+    uint2 *bins = (uint2 *)r->bins.p, *pairs = (uint2 *)r->pairs.p, *pairs_alt = (uint2 *)r->pairs_alt.p;
+    unsigned *rcount = (unsigned *)r->row_tile_count.p, *rcursor = (unsigned *)r->row_tile_cursor.p;
+    int *roff = (int *)r->row_tile_offset.p, *ioff = (int *)r->img_tile_offset.p, *merged = (int *)r->merged.p;
+    // background once per view, links once per image
+    const SasRowSpan span_bg{0, r->n_bg, C, 0, 0};
+    const SasRowSpan span_dy{r->n_bg, r->n_dyn, I, C, (long long)C * r->n_bg};
 
 #define SAS_STAGE(i) do { if (r->stage_timing) SAS_CUDA(r, cudaEventRecord(r->stage_ev[i], st)); } while (0)
     SAS_STAGE(0);
-    SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, N, r->sh_degree,
-                                   r->L > 0 ? r->link_poses : nullptr, r->L, r->cams, I, W, H, tw, th, (SasRecord *)r->rec.p,
-                                   (uint2 *)r->bins.p, (unsigned *)r->tile_count.p, r->counters, st));
-    launches += 1;
+    for (const SasRowSpan &sp : {span_bg, span_dy}) {
+        if (sp.n <= 0) continue;
+        SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
+                                       r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, rcount,
+                                       r->counters, st));
+        launches += 1;
+    }
     SAS_STAGE(1);
-    SAS_CUDA(r, sas_launch_scan((const unsigned *)r->tile_count.p, (int)IT, (int *)r->tile_offset.p, (unsigned *)r->block_sums.p,
-                                r->counters, r->max_isects, st, &launches));
+    SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st, &launches));
+    SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
+                                &launches));
     SAS_STAGE(2);
-    SAS_CUDA(r, sas_launch_emit((const uint2 *)r->bins.p, N, I, tw, th, (const int *)r->tile_offset.p, (unsigned *)r->tile_cursor.p,
-                                (uint2 *)r->pairs.p, r->max_isects, st));
-    launches += 1;
+    for (const SasRowSpan &sp : {span_bg, span_dy}) {
+        if (sp.n <= 0) continue;
+        SAS_CUDA(r, sas_launch_emit(bins, sp, tw, th, roff, rcursor, pairs, r->max_isects, st));
+        launches += 1;
+    }
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort((uint2 *)r->pairs.p, (uint2 *)r->pairs_alt.p, (const int *)r->tile_offset.p, (int)IT,
-                                     (int *)r->sorted_gid.p, r->max_isects, st, &launches));
-    // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (int)RT, r->max_isects, st, &launches));
+    SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects, st));
+    launches += 1;
     SAS_STAGE(4);
+    // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
-    SAS_CUDA(r, sas_launch_composite((const SasRecord *)r->rec.p, (const int *)r->sorted_gid.p, (const int *)r->tile_offset.p, N, I, W,
-                                     H, tw, th, b0, b1, b2, d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, r->counters,
-                                     st));
+    SAS_CUDA(r, sas_launch_composite(rec, merged, ioff, r->view_of_image, r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, d_rgb, d_depth,
+                                     d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, r->counters, st));
     launches += 1;
     SAS_STAGE(5);
     if (ns) {
@@ -371,12 +427,13 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
     SasCounters c;
     SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
     out->n_isects = (int64_t)c.n_isects;
-    out->n_visible = (int64_t)c.n_visible;
+    out->n_isects_src = (int64_t)c.n_isects_src;
+    out->n_visible_src = (int64_t)c.n_visible_src;
     out->n_staged = (int64_t)c.n_staged;
     out->max_tile_list = (int64_t)c.max_tile_list;
     out->overflow = (int32_t)c.overflow;
-    out->n_images = r->I; out->n_gaussians = r->N; out->width = r->W; out->height = r->H;
-    out->tile_w = r->tile_w; out->tile_h = r->tile_h;
+    out->n_images = r->I; out->n_views = r->C; out->n_gaussians = r->N; out->n_background = r->n_bg;
+    out->width = r->W; out->height = r->H; out->tile_w = r->tile_w; out->tile_h = r->tile_h;
     return SAS_OK;
 }
 
@@ -385,18 +442,20 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
     if (!r->rendered) return fail(r, SAS_ESTATE, "sas_debug_fetch: nothing rendered yet");
     SAS_CUDA(r, cudaSetDevice(r->device));
     SAS_CUDA(r, cudaDeviceSynchronize());
-    const size_t IN = (size_t)r->I * r->N, IT = (size_t)r->I * r->tile_w * r->tile_h;
+    const size_t T = (size_t)r->tile_w * r->tile_h;
+    const size_t n_rec = (size_t)r->C * r->n_bg + (size_t)r->I * r->n_dyn, IT = (size_t)r->I * T;
     const void *src = nullptr;
     size_t avail = 0;
     switch (what) {
-        case SAS_DBG_RECORDS: src = r->rec.p; avail = IN * sizeof(SasRecord); break;
-        case SAS_DBG_BINS: src = r->bins.p; avail = IN * sizeof(uint2); break;
-        case SAS_DBG_TILE_OFFSETS: src = r->tile_offset.p; avail = (IT + 1) * 4; break;
+        case SAS_DBG_RECORDS: src = r->rec.p; avail = n_rec * sizeof(SasRecord); break;
+        case SAS_DBG_BINS: src = r->bins.p; avail = n_rec * sizeof(uint2); break;
+        case SAS_DBG_TILE_OFFSETS: src = r->img_tile_offset.p; avail = (IT + 1) * 4; break;
+        case SAS_DBG_VIEW_OF_IMAGE: src = r->view_of_image; avail = (size_t)r->I * 4; break;
         case SAS_DBG_SORTED_GIDS: {
             SasCounters c;
             SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
             long long m = (long long)c.n_isects < r->max_isects ? (long long)c.n_isects : r->max_isects;
-            src = r->sorted_gid.p; avail = (size_t)m * 4;
+            src = r->merged.p; avail = (size_t)m * 4;
             break;
         }
         default: return fail(r, SAS_EINVAL, "sas_debug_fetch: unknown item");

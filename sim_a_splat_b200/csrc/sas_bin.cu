@@ -1,15 +1,17 @@
-// sas_bin.cu -- K2 exclusive scan of the per-(image,tile) counts (= isect_offsets, gsplat
-// _isect_offset_encode) with warp-shuffle prefix sums, and K3 emission of (depth bits, gaussian id)
-// pairs into each (image,tile) bucket.
+// sas_bin.cu -- K2 exclusive scans of per-(row,tile) counts with warp-shuffle prefix sums,
+// K3 emission of (depth bits, gaussian id) pairs into each (row,tile) bucket, and K5 the merge of
+// every image's background bucket (its view's) with its link bucket.
 //
 // Together with sas_sort.cu this is an MSD radix sort of gsplat's 64-bit key
 // (image | tile | fp32 depth bits): the (image,tile) digit is resolved here by a counting
-// partition (bucket = digit), the 32 depth bits by 8-bit LSD passes in shared memory.  The
-// resulting order is bit-identical to a stable sort of the full key with emission in ascending
-// Gaussian index, because ties on depth are broken by Gaussian id in sas_sort.cu.
+// partition (bucket = digit), the 32 depth bits by 8-bit LSD passes in shared memory
+// (sas_sort.cu).  The merged order is bit-identical to a stable sort of the full key with
+// emission in ascending Gaussian index: ties on depth are broken by Gaussian id inside a bucket
+// (sas_sort.cu) and background-before-link across the two buckets (background ids are the lower
+// ones in canonical order).  The scan of the merged counts IS gsplat's isect_offsets.
 //
-// HBM traffic: scan 8 B per (image,tile); emit reads 8 B per (image,gaussian), writes 8 B per
-// intersection.
+// HBM traffic: scan 8 B per bucket; emit reads 8 B per (row,gaussian), writes 8 B per bucket
+// entry; merge reads 8 B per merged intersection and writes 4 B.
 #include "sas_common.cuh"
 
 namespace {
@@ -46,26 +48,39 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *t
     return pre + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const unsigned *__restrict__ in, int n, unsigned *__restrict__ block_sums,
-                                                                SasCounters *counters) {
+// The value scanned at position idx: either the raw per-(row,tile) count, or (merged mode,
+// view_of_image != nullptr) the size of image i's merged tile list = its view's background
+// bucket + its own link bucket.
+__device__ __forceinline__ unsigned scan_value(const unsigned *__restrict__ counts, int idx, const int *__restrict__ view_of_image,
+                                               int C, int T) {
+    if (view_of_image == nullptr) return counts[idx];
+    const int i = idx / T, t = idx - i * T;
+    return counts[(size_t)view_of_image[i] * T + t] + counts[(size_t)(C + i) * T + t];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const unsigned *__restrict__ in, int n, const int *__restrict__ view_of_image,
+                                                                int C, int T, unsigned *__restrict__ block_sums, SasCounters *counters) {
     __shared__ unsigned wsum[8];
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned s = 0, mx = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        unsigned v = (base + k < n) ? in[base + k] : 0u;
+        unsigned v = (base + k < n) ? scan_value(in, base + k, view_of_image, C, T) : 0u;
         s += v;
         mx = max(mx, v);
     }
     unsigned tot;
     block_exclusive_scan(s, &tot, wsum);
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&counters->max_tile_list, mx);
+    if (view_of_image != nullptr) {  // longest merged list (diagnostic)
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0 && mx) atomicMax(&counters->max_tile_list, mx);
+    }
     if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
 // single block: in-place exclusive scan of block_sums[nb]; writes the grand total and the overflow flag
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partials(unsigned *block_sums, int nb, SasCounters *counters, long long max_isects) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials(unsigned *block_sums, int nb, SasCounters *counters, long long capacity,
+                                                              int merged) {
     __shared__ unsigned wsum[8];
     unsigned long long carry = 0;
     for (int base = 0; base < nb; base += SCAN_THREADS) {
@@ -77,19 +92,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_partials(unsigned *block_su
         carry += tot;
     }
     if (threadIdx.x == 0) {
-        counters->n_isects = carry;
-        counters->overflow = (carry > (unsigned long long)max_isects) ? 1u : 0u;
+        if (merged) counters->n_isects = carry; else counters->n_isects_src = carry;
+        if (carry > (unsigned long long)capacity) atomicOr(&counters->overflow, merged ? 2u : 1u);
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_final(const unsigned *__restrict__ in, int n, const unsigned *__restrict__ block_sums,
-                                                           int *__restrict__ out, const SasCounters *counters) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final(const unsigned *__restrict__ in, int n, const int *__restrict__ view_of_image, int C,
+                                                           int T, const unsigned *__restrict__ block_sums, int *__restrict__ out,
+                                                           const SasCounters *counters) {
     __shared__ unsigned wsum[8];
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
+        v[k] = (base + k < n) ? scan_value(in, base + k, view_of_image, C, T) : 0u;
         s += v[k];
     }
     unsigned tot;
@@ -100,44 +116,101 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final(const unsigned *__res
         ex += v[k];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long m = counters->n_isects;
+        unsigned long long m = view_of_image != nullptr ? counters->n_isects : counters->n_isects_src;
         out[n] = (int)(m > 0x7fffffffull ? 0x7fffffffull : m);
     }
 }
 
-__global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bins, int N, int tile_w, int tile_h,
-                                                   const int *__restrict__ tile_offset, unsigned int *__restrict__ tile_cursor,
-                                                   uint2 *__restrict__ pairs, long long max_isects) {
-    const int g = blockIdx.x * 256 + threadIdx.x;
-    const int im = blockIdx.y;
-    if (g >= N) return;
-    const uint2 bn = __ldg(bins + (size_t)im * N + g);
+__global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bins, SasRowSpan span, int tile_w, int tile_h,
+                                                   const int *__restrict__ row_tile_offset, unsigned int *__restrict__ row_tile_cursor,
+                                                   uint2 *__restrict__ pairs, long long capacity) {
+    const int local = blockIdx.x * 256 + threadIdx.x;
+    const int row = blockIdx.y;
+    if (local >= span.n) return;
+    const uint2 bn = __ldg(bins + (size_t)span.rec0 + (size_t)row * span.n + local);
     if (bn.x == 0u) return;  // culled (a visible Gaussian always has x1 >= 1)
     const int x0 = bn.x & 0xff, y0 = (bn.x >> 8) & 0xff, x1 = (bn.x >> 16) & 0xff, y1 = bn.x >> 24;
-    const size_t tbase = (size_t)im * tile_w * tile_h;
+    const size_t tbase = (size_t)(span.row0 + row) * tile_w * tile_h;
+    const unsigned gid = (unsigned)(span.g0 + local);  // canonical Gaussian index
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) {
             const size_t t = tbase + (size_t)y * tile_w + x;
-            const long long pos = (long long)__ldg(tile_offset + t) + (long long)atomicAdd(tile_cursor + t, 1u);
-            if (pos < max_isects) pairs[pos] = make_uint2(bn.y, (unsigned)g);
+            const long long pos = (long long)__ldg(row_tile_offset + t) + (long long)atomicAdd(row_tile_cursor + t, 1u);
+            if (pos < capacity) pairs[pos] = make_uint2(bn.y, gid);
         }
+}
+
+// K5: merged[image,tile] = stable merge of the view's sorted background bucket and the image's
+// sorted link bucket, by depth bits, background first on ties.  Rank-based: every element finds
+// its output slot with one binary search in the other list (the link list's keys are staged in
+// shared memory, it is the short one).
+constexpr int MERGE_THREADS = 128;
+constexpr int MERGE_SMEM_KEYS = 2048;
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
+                                                              const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
+                                                              int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all) {
+    __shared__ unsigned dkeys[MERGE_SMEM_KEYS];
+    const int t = blockIdx.x, i = blockIdx.y;
+    const size_t bb = (size_t)view_of_image[i] * T + t, db = (size_t)(C + i) * T + t;
+    long long b0 = row_tile_offset[bb], b1 = row_tile_offset[bb + 1];
+    long long d0 = row_tile_offset[db], d1 = row_tile_offset[db + 1];
+    const long long o0 = img_tile_offset[(size_t)i * T + t];
+    if (b0 < 0 || b1 < b0 || d0 < 0 || d1 < d0 || o0 < 0) return;
+    if (b1 > cap_src) b1 = cap_src;
+    if (d1 > cap_src) d1 = cap_src;
+    const int nb = b1 > b0 ? (int)(b1 - b0) : 0, nd = d1 > d0 ? (int)(d1 - d0) : 0;
+    const uint2 *bgp = pairs + b0, *dyp = pairs + d0;
+    const bool staged = nd <= MERGE_SMEM_KEYS;
+    if (staged)
+        for (int j = threadIdx.x; j < nd; j += MERGE_THREADS) dkeys[j] = dyp[j].x;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += MERGE_THREADS) {
+        const uint2 p = bgp[k];
+        int lo = 0, hi = nd;  // link entries strictly nearer than this background entry
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const unsigned key = staged ? dkeys[mid] : dyp[mid].x;
+            if (key < p.x) lo = mid + 1; else hi = mid;
+        }
+        const long long pos = o0 + k + lo;
+        if (pos < cap_all) merged[pos] = (int)p.y;
+    }
+    for (int j = threadIdx.x; j < nd; j += MERGE_THREADS) {
+        const uint2 p = dyp[j];
+        int lo = 0, hi = nb;  // background entries at least as near as this link entry
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (bgp[mid].x <= p.x) lo = mid + 1; else hi = mid;
+        }
+        const long long pos = o0 + j + lo;
+        if (pos < cap_all) merged[pos] = (int)p.y;
+    }
 }
 
 }  // namespace
 
-cudaError_t sas_launch_scan(const unsigned int *tile_count, int n, int *tile_offset, unsigned int *block_sums,
-                            SasCounters *counters, long long max_isects, cudaStream_t st, int *n_launches) {
+cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,
+                            unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches) {
     const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_block_sums<<<nb, SCAN_THREADS, 0, st>>>(tile_count, n, block_sums, counters);
-    scan_partials<<<1, SCAN_THREADS, 0, st>>>(block_sums, nb, counters, max_isects);
-    scan_final<<<nb, SCAN_THREADS, 0, st>>>(tile_count, n, block_sums, tile_offset, counters);
+    scan_block_sums<<<nb, SCAN_THREADS, 0, st>>>(counts, n, view_of_image, C, T, block_sums, counters);
+    scan_partials<<<1, SCAN_THREADS, 0, st>>>(block_sums, nb, counters, capacity, view_of_image != nullptr ? 1 : 0);
+    scan_final<<<nb, SCAN_THREADS, 0, st>>>(counts, n, view_of_image, C, T, block_sums, offsets, counters);
     if (n_launches) *n_launches += 3;
     return cudaGetLastError();
 }
 
-cudaError_t sas_launch_emit(const uint2 *bins, int N, int I, int tile_w, int tile_h, const int *tile_offset,
-                            unsigned int *tile_cursor, uint2 *pairs, long long max_isects, cudaStream_t st) {
-    dim3 grid((N + 255) / 256, I);
-    emit_kernel<<<grid, 256, 0, st>>>(bins, N, tile_w, tile_h, tile_offset, tile_cursor, pairs, max_isects);
+cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,
+                            unsigned int *row_tile_cursor, uint2 *pairs, long long capacity, cudaStream_t st) {
+    if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
+    dim3 grid((span.n + 255) / 256, span.rows);
+    emit_kernel<<<grid, 256, 0, st>>>(bins, span, tile_w, tile_h, row_tile_offset, row_tile_cursor, pairs, capacity);
+    return cudaGetLastError();
+}
+
+cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, cudaStream_t st) {
+    dim3 grid(T, I);
+    merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src, cap_all);
     return cudaGetLastError();
 }

@@ -7,6 +7,14 @@
 // --use_fast_math).  No hardware approximation (ex2.approx, rsqrt, rcp) is used
 // anywhere that feeds an integer decision (radii, tile ids, depth keys, the
 // alpha / transmittance tests).
+//
+// Work decomposition (DESIGN.md "Views and buckets"): images that share a camera
+// (same viewmat and K, e.g. the fixed camera of 256 parallel envs) share one
+// VIEW.  Background Gaussians (link_id < 0, the first n_bg in canonical order)
+// are projected, binned and depth-sorted once per view; link Gaussians once per
+// image; the two sorted lists of every (image, tile) are merged into the exact
+// order a global stable sort of gsplat's (image|tile|depth) keys would give.
+// "Rows" below are the C view rows followed by the I image rows.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,18 +32,18 @@
 // alpha test below it is unchanged.
 #define SAS_SIGMA_SKIP 5.55f
 
-// Per-image camera block, filled on the host by sas_set_cameras.
+// Per-row camera block, filled on the host by sas_set_cameras.
 struct SasCamera {
     float vm[12];     // world->camera rows 0..2 of the 4x4 (row-major): R | t
     float fx, fy, cx, cy;
     float campos[3];  // camera origin in world, -R^T t computed in fp64 on the host
-    int32_t env;      // env whose link poses this image uses
+    int32_t env;      // env whose link poses this image uses (image rows only)
     // gsplat _persp_proj clamp limits, computed once per camera on the host with the same
     // individually rounded fp32 operations the oracle performs per Gaussian
     float lim_x_pos, lim_x_neg, lim_y_pos, lim_y_neg;
 };
 
-// Projected Gaussian, 48 B, written per visible (image, gaussian).
+// Projected Gaussian, 48 B, written per visible (row, gaussian).
 struct __align__(16) SasRecord {
     float4 a;  // m2x, m2y, 0.5*conic_a, conic_b
     float4 b;  // 0.5*conic_c, opacity, radius_x, radius_y
@@ -73,27 +81,40 @@ __device__ __forceinline__ void sas_cp_async_wait() {
 
 // Device-side counters of one render call.
 struct SasCounters {
-    unsigned long long n_isects;
-    unsigned long long n_visible;
-    unsigned long long n_staged;
-    unsigned int max_tile_list;
-    unsigned int overflow;
+    unsigned long long n_isects_src;   // bucket entries emitted (background per view + links per image)
+    unsigned long long n_isects;       // merged per-image intersections (= gsplat's n_isects)
+    unsigned long long n_visible_src;  // projected records written
+    unsigned long long n_staged;       // records the compositor staged into shared memory
+    unsigned int max_tile_list;        // longest merged (image,tile) list
+    unsigned int overflow;             // bit 0: source pairs exceeded capacity, bit 1: merged ids exceeded capacity
+};
+
+// What one projection / emission launch covers: a contiguous Gaussian range for a set of rows.
+struct SasRowSpan {
+    int g0;          // first canonical Gaussian index of the range
+    int n;           // Gaussians in the range
+    int rows;        // number of rows (views for the background span, images for the link span)
+    int row0;        // index of the span's first row among all rows (0 for views, C for images)
+    long long rec0;  // offset of the span's first record / bin in the rec / bins arrays
 };
 
 // Launchers (each returns the cudaError_t of the launch).
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
-                               int n_pad, int N, int sh_degree, const float *link_poses, int L, const SasCamera *cams,
-                               int I, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *tile_count, SasCounters *counters, cudaStream_t st);
-cudaError_t sas_launch_scan(const unsigned int *tile_count, int n, int *tile_offset, unsigned int *block_sums,
-                            SasCounters *counters, long long max_isects, cudaStream_t st, int *n_launches);
-cudaError_t sas_launch_emit(const uint2 *bins, int N, int I, int tile_w, int tile_h, const int *tile_offset,
-                            unsigned int *tile_cursor, uint2 *pairs, long long max_isects, cudaStream_t st);
-cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *tile_offset, int n_buckets, int *sorted_gid,
-                                 long long max_isects, cudaStream_t st, int *n_launches);
-cudaError_t sas_launch_composite(const SasRecord *rec, const int *sorted_gid, const int *tile_offset, int N, int I, int W,
-                                 int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, float *rgb, float *depth,
-                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, SasCounters *counters,
-                                 cudaStream_t st);
+                               int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
+                               SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
+                               unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st);
+cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,
+                            unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,
+                            unsigned int *row_tile_cursor, uint2 *pairs, long long capacity, cudaStream_t st);
+cudaError_t sas_sort_init();
+cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, int n_buckets, long long capacity,
+                                 cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, cudaStream_t st);
+cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const int *img_tile_offset, const int *view_of_image,
+                                 int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1,
+                                 float bg2, float *rgb, float *depth, float *alpha, uint8_t *rgb_u8, int *n_contrib,
+                                 long long cap_all, SasCounters *counters, cudaStream_t st);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

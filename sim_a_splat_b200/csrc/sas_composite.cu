@@ -29,7 +29,8 @@ __device__ __forceinline__ unsigned char to_u8(float v) {
 }
 
 __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ sorted_gid,
-                                                       const int *__restrict__ tile_offset, int N, int W, int H, int tile_w, int tile_h,
+                                                       const int *__restrict__ tile_offset, const int *__restrict__ view_of_image,
+                                                       int n_bg, int n_dyn, int C, int W, int H, int tile_w, int tile_h,
                                                        float bg0, float bg1, float bg2, float *__restrict__ out_rgb,
                                                        float *__restrict__ out_depth, float *__restrict__ out_alpha,
                                                        uint8_t *__restrict__ out_u8, int *__restrict__ out_nc, long long max_isects,
@@ -46,7 +47,11 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
     if (off > end) off = end;
     const int n = (int)(end - off);
     const int *gids = sorted_gid + off;
-    const SasRecord *irec = rec + (size_t)im * N;
+    // background records live per view, link records per image (sas_common.cuh); a merged id below
+    // n_bg selects the former.  rec_of(gid) = the record of canonical Gaussian gid for this image.
+    const SasRecord *rec_bg = rec + (size_t)view_of_image[im] * n_bg;
+    const SasRecord *rec_dy = rec + (size_t)C * n_bg + (size_t)im * n_dyn - n_bg;
+#define SAS_REC_OF(gid) (((gid) < n_bg ? rec_bg : rec_dy) + (gid))
 
     // warp footprint: 8 wide x 4 high
     const int fx = tx * SAS_TILE_PX + (warp & 1) * 8, fy = ty * SAS_TILE_PX + (warp >> 1) * 4;
@@ -65,7 +70,8 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
     // prologue: batch 0 in flight, id of batch 1 in a register
     int gid_next = 0;
     if (tid < n) {
-        const SasRecord *s = irec + __ldg(gids + tid);
+        const int g0 = __ldg(gids + tid);
+        const SasRecord *s = SAS_REC_OF(g0);
         sas_cp_async16(&stage[0][tid].a, &s->a);
         sas_cp_async16(&stage[0][tid].b, &s->b);
         sas_cp_async16(&stage[0][tid].c, &s->c);
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
         {  // batch b+1 -> other buffer; id of batch b+2 -> register
             const int e1 = (b + 1) * CB + tid;
             if (e1 < n) {
-                const SasRecord *s = irec + gid_next;
+                const SasRecord *s = SAS_REC_OF(gid_next);
                 sas_cp_async16(&stage[buf ^ 1][tid].a, &s->a);
                 sas_cp_async16(&stage[buf ^ 1][tid].b, &s->b);
                 sas_cp_async16(&stage[buf ^ 1][tid].c, &s->c);
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(CB) composite_kernel(const SasRecord *__restri
             if (__all_sync(0xffffffffu, done)) break;
         }
     }
+#undef SAS_REC_OF
     sas_cp_async_wait<0>();
     if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged);
 
@@ -176,13 +183,13 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 
 }  // namespace
 
-cudaError_t sas_launch_composite(const SasRecord *rec, const int *sorted_gid, const int *tile_offset, int N, int I, int W,
-                                 int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, float *rgb, float *depth,
-                                 float *alpha, uint8_t *rgb_u8, int *n_contrib, long long max_isects, SasCounters *counters,
-                                 cudaStream_t st) {
+cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const int *img_tile_offset, const int *view_of_image,
+                                 int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1,
+                                 float bg2, float *rgb, float *depth, float *alpha, uint8_t *rgb_u8, int *n_contrib,
+                                 long long cap_all, SasCounters *counters, cudaStream_t st) {
     dim3 grid(tile_w * tile_h, I);
-    composite_kernel<<<grid, CB, 0, st>>>(rec, sorted_gid, tile_offset, N, W, H, tile_w, tile_h, bg0, bg1, bg2, rgb, depth, alpha,
-                                          rgb_u8, n_contrib, max_isects, counters);
+    composite_kernel<<<grid, CB, 0, st>>>(rec, merged_gid, img_tile_offset, view_of_image, n_bg, n_dyn, C, W, H, tile_w, tile_h, bg0,
+                                          bg1, bg2, rgb, depth, alpha, rgb_u8, n_contrib, cap_all, counters);
     return cudaGetLastError();
 }
 

@@ -41,17 +41,20 @@ __device__ __forceinline__ void sh_bases(int deg, float x, float y, float z, flo
     b[15] = fTmpA * fC2; b[9] = fTmpA * fS2;
 }
 
+// One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
+// cameras), the link span once per IMAGE (rows = env x camera) -- see sas_common.cuh.
 template <int DEG>
 __global__ void __launch_bounds__(256)
 project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
-               const float *__restrict__ sh_planes, int n_pad, int N, const float *__restrict__ link_poses, int L,
-               const SasCamera *__restrict__ cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
-               uint2 *__restrict__ bins, unsigned int *__restrict__ tile_count, SasCounters *counters) {
-    const int g = blockIdx.x * 256 + threadIdx.x;
-    const int im = blockIdx.y;
-    if (g >= N) return;
-    const size_t ig = (size_t)im * N + g;
-    const SasCamera *cam = cams + im;
+               const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
+               const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
+               uint2 *__restrict__ bins, unsigned int *__restrict__ row_tile_count, SasCounters *counters) {
+    const int local = blockIdx.x * 256 + threadIdx.x;
+    const int row = blockIdx.y;
+    if (local >= span.n) return;
+    const int g = span.g0 + local;
+    const size_t ig = (size_t)span.rec0 + (size_t)row * span.n + local;
+    const SasCamera *cam = row_cams + span.row0 + row;
 
     const float4 mo = __ldg(mean_op + g);
     const float4 qq = __ldg(quat + g);
@@ -201,23 +204,27 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
     r.c = make_float4(col[0], col[1], col[2], czm);
     rec[ig] = r;
 
-    // per-(image,tile) counts; the exclusive scan of these is isect_offsets (S7)
-    unsigned int *tc = tile_count + (size_t)im * tile_w * tile_h;
+    // per-(row,tile) counts; their exclusive scan gives the bucket offsets
+    unsigned int *tc = row_tile_count + (size_t)(span.row0 + row) * tile_w * tile_h;
     for (int y = y0; y < y1; y++)
         for (int x = x0; x < x1; x++) atomicAdd(tc + y * tile_w + x, 1u);
-    atomicAdd(&counters->n_visible, 1ull);
+    {  // one counter update per warp instead of one per thread
+        const unsigned m = __activemask();
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&counters->n_visible_src, (unsigned long long)__popc(m));
+    }
 }
 
 }  // namespace
 
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
-                               int n_pad, int N, int sh_degree, const float *link_poses, int L, const SasCamera *cams,
-                               int I, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *tile_count, SasCounters *counters, cudaStream_t st) {
-    dim3 grid((N + 255) / 256, I);
-#define SAS_PROJ(D)                                                                                                   \
-    project_kernel<D><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, N, link_poses, L, cams, W, H, \
-                                            tile_w, tile_h, rec, bins, tile_count, counters)
+                               int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
+                               SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
+                               unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st) {
+    if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
+    dim3 grid((span.n + 255) / 256, span.rows);
+#define SAS_PROJ(D)                                                                                                        \
+    project_kernel<D><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, H, \
+                                            tile_w, tile_h, rec, bins, row_tile_count, counters)
     switch (sh_degree) {
         case 0: SAS_PROJ(0); break;
         case 1: SAS_PROJ(1); break;

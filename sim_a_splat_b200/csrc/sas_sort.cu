@@ -6,23 +6,22 @@
 // histograms, a warp-shuffle scan across digits, and a stable multi-split that ranks equal
 // digits inside a warp with match.any + popc), equal-depth runs are then ordered by Gaussian id
 // (which is what a stable sort with ascending-Gaussian emission produces in the reference), and
-// the sorted Gaussian ids are written back.  Passes whose digit is uniform over the bucket (the
-// exponent byte, usually) are skipped.
+// the sorted (depth, id) pairs are written back in place.  Passes whose digit is uniform over the
+// bucket (the exponent byte, usually) are skipped.
 //
-// Buckets are dispatched by size class (shared-memory footprint = occupancy): <=2048, <=6144,
-// <=12288 entries in shared memory; larger buckets run the same passes directly on global memory
-// (ping-pong with a second pair buffer) in one CTA.
+// Buckets are dispatched by size class (threads and shared-memory footprint = occupancy):
+// <=512 entries (4 warps), <=2048 (8 warps), <=6144 and <=12288 (16 warps) in shared memory;
+// larger buckets run the same passes directly on global memory (ping-pong with a second pair
+// buffer) in one CTA.
 //
-// HBM traffic: 8 B read + 4 B written per intersection.
+// HBM traffic: 8 B read + 8 B written per bucket entry.
 #include "sas_common.cuh"
 
 namespace {
 
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
-
+template <int NT>
 struct alignas(16) SortShared {
-    unsigned hist[SORT_WARPS][256];
+    unsigned hist[NT / 32][256];
     unsigned tot[256];
     unsigned wsum[8];
     int uniform;
@@ -30,7 +29,9 @@ struct alignas(16) SortShared {
 
 // One stable LSD pass src -> dst on bits [shift, shift+8) of .x.  Returns false (and leaves dst
 // untouched) if every key has the same digit.
-__device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortShared &sh) {
+template <int NT>
+__device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortShared<NT> &sh) {
+    constexpr int SORT_THREADS = NT, SORT_WARPS = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&sh.hist[0][0])[i] = 0u;
     if (tid == 0) sh.uniform = 0;
@@ -40,35 +41,41 @@ __device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortS
     const int lo = min(n, warp * seg), hi = min(n, lo + seg);
     for (int i = lo + lane; i < hi; i += 32) atomicAdd(&sh.hist[warp][(src[i].x >> shift) & 0xffu], 1u);
     __syncthreads();
-    if (tid < 256) {
+    // per digit: exclusive prefix over the warps, digit total
+    for (int d = tid; d < 256; d += SORT_THREADS) {
         unsigned run = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) {
-            unsigned t = sh.hist[w][tid];
-            sh.hist[w][tid] = run;
+            unsigned t = sh.hist[w][d];
+            sh.hist[w][d] = run;
             run += t;
         }
+        sh.tot[d] = run;
         if (run == (unsigned)n) sh.uniform = 1;
-        // exclusive scan of tot over the 256 digits (8 warps)
-        unsigned inc = run;
+    }
+    __syncthreads();
+    const int uniform = sh.uniform;  // read before anyone can re-enter and reset it
+    // warp 0: exclusive scan of the 256 digit totals (8 per lane + a warp-shuffle scan)
+    if (warp == 0) {
+        unsigned v[8], s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] = sh.tot[lane * 8 + k]; s += v[k]; }
+        unsigned inc = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += t;
         }
-        if (lane == 31) sh.wsum[warp] = inc;
-        sh.tot[tid] = inc - run;  // exclusive within the warp
+        unsigned ex = inc - s;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { sh.tot[lane * 8 + k] = ex; ex += v[k]; }
     }
     __syncthreads();
-    const int uniform = sh.uniform;  // read before anyone can re-enter and reset it
-    __syncthreads();
     if (uniform) return false;
-    if (tid < 256) {
-        unsigned pre = 0;
-        for (int w = 0; w < warp; w++) pre += sh.wsum[w];
-        const unsigned base = sh.tot[tid] + pre;
+    for (int d = tid; d < 256; d += SORT_THREADS) {
+        const unsigned base = sh.tot[d];
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) sh.hist[w][tid] += base;
+        for (int w = 0; w < SORT_WARPS; w++) sh.hist[w][d] += base;
     }
     __syncthreads();
     // stable multi-split: hist[warp][digit] is the running absolute position
@@ -97,8 +104,9 @@ __device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortS
 }
 
 // Equal-depth runs -> ascending Gaussian id (runs are disjoint; the thread at a run's start sorts it).
+template <int NT>
 __device__ void fix_ties(uint2 *a, int n) {
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+    for (int i = threadIdx.x; i < n; i += NT) {
         const unsigned k = a[i].x;
         if ((i == 0 || a[i - 1].x != k) && i + 1 < n && a[i + 1].x == k) {
             int j = i + 1;
@@ -114,12 +122,12 @@ __device__ void fix_ties(uint2 *a, int n) {
     __syncthreads();
 }
 
-template <bool IN_GLOBAL>
-__global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(uint2 *pairs, uint2 *pairs_alt,
-                                                                 const int *__restrict__ tile_offset, int *__restrict__ sorted_gid,
-                                                                 int lo_size, int hi_size, long long max_isects) {
+template <int NT, bool IN_GLOBAL>
+__global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pairs_alt, const int *__restrict__ tile_offset,
+                                                       int lo_size, int hi_size, long long max_isects) {
+    constexpr int SORT_THREADS = NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SortShared &sh = *reinterpret_cast<SortShared *>(smem_raw);
+    SortShared<NT> &sh = *reinterpret_cast<SortShared<NT> *>(smem_raw);
     const int b = blockIdx.x;
     long long off = tile_offset[b], end = tile_offset[b + 1];
     if (off < 0 || end < off) return;
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(uint2 *pairs, u
         src = pairs + off;
         dst = pairs_alt + off;
     } else {
-        src = reinterpret_cast<uint2 *>(smem_raw + sizeof(SortShared));
+        src = reinterpret_cast<uint2 *>(smem_raw + sizeof(SortShared<NT>));
         dst = src + (hi_size - 1);
         for (int i = threadIdx.x; i < n; i += SORT_THREADS) src[i] = pairs[off + i];
     }
@@ -144,34 +152,31 @@ __global__ void __launch_bounds__(SORT_THREADS) tile_sort_kernel(uint2 *pairs, u
                 uint2 *t = src; src = dst; dst = t;
             }
         }
-        fix_ties(src, n);
+        fix_ties<NT>(src, n);
     }
-    for (int i = threadIdx.x; i < n; i += SORT_THREADS) sorted_gid[off + i] = (int)src[i].y;
+    // sorted pairs back in place (the merge kernel needs the depth keys as well as the ids)
+    if (src != pairs + off)
+        for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[off + i] = src[i];
 }
 
 }  // namespace
 
-cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *tile_offset, int n_buckets, int *sorted_gid,
-                                 long long max_isects, cudaStream_t st, int *n_launches) {
+template <int NT>
+static size_t sort_smem(int cap) { return sizeof(SortShared<NT>) + 2 * (size_t)cap * sizeof(uint2); }
+
+cudaError_t sas_sort_init() {
+    return cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem<512>(12288));
+}
+
+cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, int n_buckets, long long capacity,
+                                 cudaStream_t st, int *n_launches) {
     // size classes [lo, hi): shared memory = SortShared + 2*(hi-1) pairs
-    static const int bounds[4] = {1, 2049, 6145, 12289};
-    static bool attr_set_dev[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    bool &attr_set = attr_set_dev[dev & 63];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(SortShared) + 2 * (size_t)(bounds[3] - 1) * sizeof(uint2)));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    for (int c = 0; c < 3; c++) {
-        const size_t smem = sizeof(SortShared) + 2 * (size_t)(bounds[c + 1] - 1) * sizeof(uint2);
-        tile_sort_kernel<false><<<n_buckets, SORT_THREADS, smem, st>>>(pairs, pairs_alt, tile_offset, sorted_gid, bounds[c],
-                                                                      bounds[c + 1], max_isects);
-    }
-    tile_sort_kernel<true><<<n_buckets, SORT_THREADS, sizeof(SortShared), st>>>(pairs, pairs_alt, tile_offset, sorted_gid, bounds[3],
-                                                                               0x7fffffff, max_isects);
-    if (n_launches) *n_launches += 4;
+    tile_sort_kernel<128, false><<<n_buckets, 128, sort_smem<128>(512), st>>>(pairs, pairs_alt, row_tile_offset, 1, 513, capacity);
+    tile_sort_kernel<256, false><<<n_buckets, 256, sort_smem<256>(2048), st>>>(pairs, pairs_alt, row_tile_offset, 513, 2049, capacity);
+    tile_sort_kernel<512, false><<<n_buckets, 512, sort_smem<512>(6144), st>>>(pairs, pairs_alt, row_tile_offset, 2049, 6145, capacity);
+    tile_sort_kernel<512, false><<<n_buckets, 512, sort_smem<512>(12288), st>>>(pairs, pairs_alt, row_tile_offset, 6145, 12289, capacity);
+    tile_sort_kernel<512, true><<<n_buckets, 512, sizeof(SortShared<512>), st>>>(pairs, pairs_alt, row_tile_offset, 12289, 0x7fffffff,
+                                                                               capacity);
+    if (n_launches) *n_launches += 5;
     return cudaGetLastError();
 }

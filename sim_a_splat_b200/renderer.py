@@ -168,18 +168,31 @@ class SplatRenderer:
 
     # -- parity-test access to intermediates ------------------------------------------------
     def debug_intermediates(self) -> dict:
-        """Intermediates of the last render in the oracle's layout (numpy, host)."""
+        """Intermediates of the last render in the oracle's per-(image, gaussian) layout (numpy, host).
+        The library keeps background records once per view and link records once per image; they are
+        re-assembled here."""
         s = self.stats()
-        I, N = self.I, self.N
+        I, N, C, nbg = self.I, self.N, s["n_views"], s["n_background"]
+        ndy = N - nbg
         tw, th = s["tile_w"], s["tile_h"]
         T = tw * th
         M = min(s["n_isects"], 2**31 - 16)
-        rec = np.empty((I, N, 12), dtype=np.float32)
-        bins = np.empty((I, N, 2), dtype=np.uint32)
+        n_rec = C * nbg + I * ndy
+        rec_raw = np.empty((n_rec, 12), dtype=np.float32)
+        bins_raw = np.empty((n_rec, 2), dtype=np.uint32)
         offs = np.empty(I * T + 1, dtype=np.int32)
         gids = np.empty(M, dtype=np.int32)
-        for what, arr in ((L.SAS_DBG_RECORDS, rec), (L.SAS_DBG_BINS, bins), (L.SAS_DBG_TILE_OFFSETS, offs), (L.SAS_DBG_SORTED_GIDS, gids)):
+        voi = np.empty(I, dtype=np.int32)
+        for what, arr in ((L.SAS_DBG_RECORDS, rec_raw), (L.SAS_DBG_BINS, bins_raw), (L.SAS_DBG_TILE_OFFSETS, offs),
+                          (L.SAS_DBG_SORTED_GIDS, gids), (L.SAS_DBG_VIEW_OF_IMAGE, voi)):
             L.check(self._lib, self._h, self._lib.sas_debug_fetch(self._h, what, arr.ctypes.data, arr.nbytes))
+
+        def per_image(raw):
+            bg = raw[: C * nbg].reshape(C, nbg, raw.shape[1])[voi]
+            dy = raw[C * nbg:].reshape(I, ndy, raw.shape[1])
+            return np.concatenate([bg, dy], axis=1)
+
+        rec, bins = per_image(rec_raw), per_image(bins_raw)
         rect = np.stack([bins[..., 0] & 0xff, (bins[..., 0] >> 8) & 0xff, (bins[..., 0] >> 16) & 0xff, bins[..., 0] >> 24], axis=-1).astype(np.int32)
         vis = bins[..., 0] != 0
         tiles = ((rect[..., 2] - rect[..., 0]) * (rect[..., 3] - rect[..., 1])).astype(np.int32)
@@ -198,5 +211,5 @@ class SplatRenderer:
             radii=z(rec[..., 6:8]).astype(np.int32), means2d=z(rec[..., 0:2]), depths=z(rec[..., 11]), conics=z(conics),
             colors=z(rec[..., 8:11]), opacities=z(rec[..., 5]), tiles_per_gauss=z(tiles), tile_rect=z(rect), visible=vis,
             isect_ids=isect_ids, flatten_ids=flat.astype(np.int32), isect_offsets=offs[:-1].reshape(I, th, tw).copy(),
-            M=M, tile_bits=tile_bits, stats=s,
+            M=M, tile_bits=tile_bits, stats=s, view_of_image=voi,
         )

@@ -27,6 +27,25 @@ def test_small_scene_all_stages(deg):
     assert rep["M_ref"] > 1000
 
 
+def test_views_shared_across_envs_and_mixed_cameras():
+    """2 fixed cameras x 5 envs = 2 views / 10 images, plus one env-specific (moving) camera each:
+    background work is shared per view, results must not notice."""
+    sc = S.make_synthetic_scene(9000, 2, seed=61, link_counts=(700, 300))
+    W, H, E = 128, 96, 5
+    fixed = S.ring_cameras(2, (0, 0, 0), seed=1)
+    moving = S.ring_cameras(E, (0, 0, 0), seed=2)
+    vms, env = [], []
+    for e in range(E):
+        vms += [fixed[0], moving[e], fixed[1]]
+        env += [e, e, e]
+    gpu, ref = run_both(sc, np.stack(vms), S.fov_intrinsics(W, H)[None], W, H, S.random_link_poses(E, 2, seed=70), env)
+    assert gpu["stats"]["n_views"] == 2 + E and gpu["stats"]["n_images"] == 3 * E
+    assert gpu["view_of_image"].tolist() == [0, 1, 2, 0, 3, 2, 0, 4, 2, 0, 5, 2, 0, 6, 2]
+    rep = compare(gpu, ref)
+    print(rep)
+    assert_parity(rep)
+
+
 def test_no_links_static_scene():
     sc = S.make_synthetic_scene(5000, 3, seed=7)
     gpu, ref = run_both(sc, S.ring_cameras(2, (0, 0, 0), seed=3), S.fov_intrinsics(96, 96)[None], 96, 96)
@@ -153,7 +172,8 @@ def test_rendering_is_deterministic_and_host_path_matches():
         assert torch.equal(a[k], c[k]), k
     # linearity in the background: rgb(bg) - rgb(0) = T * bg
     z = r.render(("rgb", "alpha"))
-    np.testing.assert_allclose((a["rgb"] - z["rgb"]).cpu().numpy(), ((1 - z["alpha"])[..., None] * 0.3).cpu().numpy(), atol=2e-7)
+    want = np.broadcast_to(((1 - z["alpha"])[..., None] * 0.3).cpu().numpy(), tuple(a["rgb"].shape))
+    np.testing.assert_allclose((a["rgb"] - z["rgb"]).cpu().numpy(), want, atol=2e-7)
     r.close()
 
 
