@@ -42,6 +42,7 @@ struct sas_renderer {
     bool cameras_set = false;
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
+    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc;
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -154,7 +155,10 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
 #define SAS_TRY(x) do { int rc_ = (x); if (rc_) return bail(rc_); } while (0)
 #define SAS_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { r->err = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(e_ == cudaErrorMemoryAllocation ? SAS_ENOMEM : SAS_ECUDA); } } while (0)
     SAS_CUDA_C(cudaSetDevice(device));
-    SAS_CUDA_C(sas_sort_init());
+    int n_sms = 0;
+    SAS_CUDA_C(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+    SAS_CUDA_C(sas_sort_init(n_sms));
+    SAS_CUDA_C(sas_composite_init(n_sms));
 
     // bring the scene to the host if needed, pack SoA, upload
     std::vector<float> h_means((size_t)N * 3), h_quats((size_t)N * 4), h_scales((size_t)N * 3), h_op(N), h_sh((size_t)N * K * 3);
@@ -204,8 +208,8 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     r->stage_bytes = sizeof(SasCamera) * 2 * cfg->max_images + sizeof(int) * cfg->max_images;
     SAS_CUDA_C(cudaMallocHost(&r->stage_host, r->stage_bytes));
     SAS_CUDA_C(cudaEventCreateWithFlags(&r->cams_copied, cudaEventDisableTiming));
-    SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters)));
-    SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters)));
+    SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
+    SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
     long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
     SAS_TRY(ensure_isects(r, m));
 #undef SAS_TRY
@@ -225,7 +229,8 @@ void sas_destroy(sas_renderer *r) {
     for (cudaEvent_t ev : r->stage_ev)
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
-                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc};
+                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc,
+                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -310,6 +315,14 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     if ((rc = ensure(r, r->img_tile_offset, (IT + 1) * 4))) return rc;
     if ((rc = ensure(r, r->block_sums, (RT / 1024 + 2) * 4))) return rc;
     if ((rc = ensure(r, r->img_max, (size_t)n_images * 4))) return rc;
+    // work lists (sas_work.cu) and the per-view tile buffers shared by the images of a view
+    const size_t VT = (size_t)C * T, VP = (size_t)C * width * height;
+    if ((rc = ensure(r, r->sort_list, RT * 4))) return rc;
+    if ((rc = ensure(r, r->comp_list, (IT + VT) * 4))) return rc;
+    if ((rc = ensure(r, r->view_needed, VT))) return rc;
+    if ((rc = ensure(r, r->v_acc, VP * 16))) return rc;
+    if ((rc = ensure(r, r->v_depth, VP * 4))) return rc;
+    if ((rc = ensure(r, r->v_nc, VP * 4))) return rc;
     return SAS_OK;
 }
 
@@ -342,7 +355,8 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
 
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_count.p, 0, RT * 4, st));
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_cursor.p, 0, RT * 4, st));
-    SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters), st));
+    SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork), st));  // counters and work lists
+    SasWork *work = reinterpret_cast<SasWork *>(r->counters + 1);
 
     SasRecord *rec = (SasRecord *)r->rec.p;
     uint2 *bins = (uint2 *)r->bins.p, *pairs = (uint2 *)r->pairs.p, *pairs_alt = (uint2 *)r->pairs_alt.p;
@@ -365,6 +379,8 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st, &launches));
     SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
                                 &launches));
+    SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, C, I, T, work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p,
+                                      (int *)r->comp_list.p, st, &launches));
     SAS_STAGE(2);
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
@@ -372,15 +388,17 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         launches += 1;
     }
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (int)RT, r->max_isects, st, &launches));
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, &launches));
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects, st));
     launches += 1;
     SAS_STAGE(4);
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
-    SAS_CUDA(r, sas_launch_composite(rec, merged, ioff, r->view_of_image, r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, d_rgb, d_depth,
-                                     d_alpha, ns ? nullptr : d_u8, d_nc, r->max_isects, r->counters, st));
-    launches += 1;
+    const SasOutputs img_out{d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc};
+    const SasViewBuf view_out{(float *)r->v_acc.p, (float *)r->v_depth.p, (int *)r->v_nc.p};
+    SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, (const int *)r->comp_list.p, work, r->n_bg,
+                                     r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, r->max_isects, r->max_isects,
+                                     r->counters, st, &launches));
     SAS_STAGE(5);
     if (ns) {
         SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, I, W, H, out->background[0], out->background[1],

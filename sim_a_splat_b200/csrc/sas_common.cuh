@@ -98,7 +98,37 @@ struct SasRowSpan {
     long long rec0;  // offset of the span's first record / bin in the rec / bins arrays
 };
 
+// Bucket-sort size classes (entries): threads / shared memory differ per class (sas_sort.cu).
+#define SAS_SORT_CLASSES 5
+#define SAS_SORT_CAP0 512
+#define SAS_SORT_CAP1 2048
+#define SAS_SORT_CAP2 5632
+#define SAS_SORT_CAP3 12288
+#define SAS_COMP_CLASSES 32
+
+// Device-side work lists of one render call (sas_work.cu); zeroed with the counters.
+struct SasWork {
+    unsigned sort_count[SAS_SORT_CLASSES], sort_start[SAS_SORT_CLASSES], sort_fill[SAS_SORT_CLASSES], sort_take[SAS_SORT_CLASSES];
+    unsigned comp_count[SAS_COMP_CLASSES], comp_start[SAS_COMP_CLASSES], comp_fill[SAS_COMP_CLASSES];
+    unsigned comp_total, comp_take;
+};
+
+// Outputs of the compositor: per-image buffers (any may be null) ...
+struct SasOutputs {
+    float *rgb, *depth, *alpha;
+    uint8_t *rgb_u8;
+    int *n_contrib;
+};
+// ... and the per-view buffers holding the background-only tiles shared by the images of a view.
+struct SasViewBuf {
+    float *acc;      // [C,H,W,4] accumulated r,g,b and the transmittance T
+    float *depth;    // [C,H,W]   expected depth
+    int *n_contrib;  // [C,H,W]
+};
+
 // Launchers (each returns the cudaError_t of the launch).
+cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, int C, int I, int T, SasWork *work,
+                                  unsigned char *view_tile_needed, int *sort_list, int *comp_list, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
@@ -107,14 +137,18 @@ cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_o
                             unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,
                             unsigned int *row_tile_cursor, uint2 *pairs, long long capacity, cudaStream_t st);
-cudaError_t sas_sort_init();
-cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, int n_buckets, long long capacity,
-                                 cudaStream_t st, int *n_launches);
+cudaError_t sas_sort_init(int n_sms);
+cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
+                                 long long capacity, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, cudaStream_t st);
-cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const int *img_tile_offset, const int *view_of_image,
-                                 int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1,
-                                 float bg2, float *rgb, float *depth, float *alpha, uint8_t *rgb_u8, int *n_contrib,
-                                 long long cap_all, SasCounters *counters, cudaStream_t st);
+cudaError_t sas_composite_init(int n_sms);
+// Composites the ordered work list (image tiles with link Gaussians + the needed view tiles), then
+// copies the view tiles into the images whose link bucket for that tile is empty.
+cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
+                                 const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
+                                 const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w,
+                                 int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out, SasViewBuf view_out,
+                                 long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

@@ -15,6 +15,8 @@
 // (written separately; see the numerics contract in sas_common.cuh).
 #include "sas_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ void sh_bases(int deg, float x, float y, float z, float *b) {
@@ -43,8 +45,8 @@ __device__ __forceinline__ void sh_bases(int deg, float x, float y, float z, flo
 
 // One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
 // cameras), the link span once per IMAGE (rows = env x camera) -- see sas_common.cuh.
-template <int DEG>
-__global__ void __launch_bounds__(256)
+template <int DEG, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
                const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
                const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
@@ -222,9 +224,22 @@ cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const 
                                unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st) {
     if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
     dim3 grid((span.n + 255) / 256, span.rows);
-#define SAS_PROJ(D)                                                                                                        \
-    project_kernel<D><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, H, \
-                                            tile_w, tile_h, rec, bins, row_tile_count, counters)
+    // SAS_PROJECT=1 (environment, read once): registers uncapped at 2 CTAs/SM so all SH loads of a thread are in
+    // flight at once; default 0 = 3-4 CTAs/SM.
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("SAS_PROJECT");
+        variant = (e && atoi(e) == 1) ? 1 : 0;
+    }
+#define SAS_PROJ(D)                                                                                                                   \
+    do {                                                                                                                              \
+        if (variant == 1)                                                                                                             \
+            project_kernel<D, 2><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, \
+                                                      H, tile_w, tile_h, rec, bins, row_tile_count, counters);                        \
+        else                                                                                                                          \
+            project_kernel<D, 3><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, \
+                                                      H, tile_w, tile_h, rec, bins, row_tile_count, counters);                        \
+    } while (0)
     switch (sh_degree) {
         case 0: SAS_PROJ(0); break;
         case 1: SAS_PROJ(1); break;

@@ -10,9 +10,10 @@
 // bucket (the exponent byte, usually) are skipped.
 //
 // Buckets are dispatched by size class (threads and shared-memory footprint = occupancy):
-// <=512 entries (4 warps), <=2048 (8 warps), <=6144 and <=12288 (16 warps) in shared memory;
+// <=512 entries (4 warps), <=2048 (8 warps), <=5632 and <=12288 (16 warps) in shared memory;
 // larger buckets run the same passes directly on global memory (ping-pong with a second pair
-// buffer) in one CTA.
+// buffer) in one CTA.  Each class is one launch of persistent CTAs that pull bucket ids from the
+// class's work list (sas_work.cu), so empty classes cost one near-empty launch.
 //
 // HBM traffic: 8 B read + 8 B written per bucket entry.
 #include "sas_common.cuh"
@@ -122,61 +123,83 @@ __device__ void fix_ties(uint2 *a, int n) {
     __syncthreads();
 }
 
+// Persistent CTAs: each pulls the next bucket of its size class from the class's work list
+// (sas_work.cu) until the list is exhausted.
 template <int NT, bool IN_GLOBAL>
 __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pairs_alt, const int *__restrict__ tile_offset,
-                                                       int lo_size, int hi_size, long long max_isects) {
+                                                       const int *__restrict__ sort_list, SasWork *work, int cls, int cap,
+                                                       long long max_isects) {
     constexpr int SORT_THREADS = NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortShared<NT> &sh = *reinterpret_cast<SortShared<NT> *>(smem_raw);
-    const int b = blockIdx.x;
-    long long off = tile_offset[b], end = tile_offset[b + 1];
-    if (off < 0 || end < off) return;
-    if (end > max_isects) end = max_isects;
-    const long long nn = end - off;
-    if (nn < (long long)lo_size || nn >= (long long)hi_size || nn <= 0) return;
-    const int n = (int)nn;
-    uint2 *src, *dst;
-    if (IN_GLOBAL) {
-        src = pairs + off;
-        dst = pairs_alt + off;
-    } else {
-        src = reinterpret_cast<uint2 *>(smem_raw + sizeof(SortShared<NT>));
-        dst = src + (hi_size - 1);
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) src[i] = pairs[off + i];
-    }
-    __syncthreads();
-    if (n > 1) {
-#pragma unroll 1
-        for (int shift = 0; shift < 32; shift += 8) {
-            if (radix_pass(src, dst, n, shift, sh)) {
-                uint2 *t = src; src = dst; dst = t;
-            }
+    __shared__ unsigned s_take;
+    const unsigned n_items = work->sort_count[cls];
+    const int *list = sort_list + work->sort_start[cls];
+    for (;;) {
+        __syncthreads();  // previous bucket fully written back; s_take free to overwrite
+        if (threadIdx.x == 0) s_take = atomicAdd(&work->sort_take[cls], 1u);
+        __syncthreads();
+        const unsigned k = s_take;
+        if (k >= n_items) break;
+        const int b = list[k];
+        long long off = tile_offset[b], end = tile_offset[b + 1];
+        if (off < 0 || end < off) continue;
+        if (end > max_isects) end = max_isects;
+        const long long nn = end - off;
+        if (nn <= 0 || (!IN_GLOBAL && nn > (long long)cap)) continue;
+        const int n = (int)nn;
+        uint2 *src, *dst;
+        if (IN_GLOBAL) {
+            src = pairs + off;
+            dst = pairs_alt + off;
+        } else {
+            src = reinterpret_cast<uint2 *>(smem_raw + sizeof(SortShared<NT>));
+            dst = src + cap;
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) src[i] = pairs[off + i];
         }
-        fix_ties<NT>(src, n);
+        __syncthreads();
+        if (n > 1) {
+#pragma unroll 1
+            for (int shift = 0; shift < 32; shift += 8) {
+                if (radix_pass(src, dst, n, shift, sh)) {
+                    uint2 *t = src; src = dst; dst = t;
+                }
+            }
+            fix_ties<NT>(src, n);
+        }
+        // sorted pairs back in place (the merge kernel needs the depth keys as well as the ids)
+        if (src != pairs + off)
+            for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[off + i] = src[i];
     }
-    // sorted pairs back in place (the merge kernel needs the depth keys as well as the ids)
-    if (src != pairs + off)
-        for (int i = threadIdx.x; i < n; i += SORT_THREADS) pairs[off + i] = src[i];
 }
+
+template <int NT>
+size_t sort_smem(int cap) { return sizeof(SortShared<NT>) + 2 * (size_t)cap * sizeof(uint2); }
+
+int g_sort_sms = 148;
 
 }  // namespace
 
-template <int NT>
-static size_t sort_smem(int cap) { return sizeof(SortShared<NT>) + 2 * (size_t)cap * sizeof(uint2); }
-
-cudaError_t sas_sort_init() {
-    return cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem<512>(12288));
+cudaError_t sas_sort_init(int n_sms) {
+    g_sort_sms = n_sms > 0 ? n_sms : 148;
+    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sort_smem<512>(SAS_SORT_CAP3));
+    return e;
 }
 
-cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, int n_buckets, long long capacity,
-                                 cudaStream_t st, int *n_launches) {
-    // size classes [lo, hi): shared memory = SortShared + 2*(hi-1) pairs
-    tile_sort_kernel<128, false><<<n_buckets, 128, sort_smem<128>(512), st>>>(pairs, pairs_alt, row_tile_offset, 1, 513, capacity);
-    tile_sort_kernel<256, false><<<n_buckets, 256, sort_smem<256>(2048), st>>>(pairs, pairs_alt, row_tile_offset, 513, 2049, capacity);
-    tile_sort_kernel<512, false><<<n_buckets, 512, sort_smem<512>(6144), st>>>(pairs, pairs_alt, row_tile_offset, 2049, 6145, capacity);
-    tile_sort_kernel<512, false><<<n_buckets, 512, sort_smem<512>(12288), st>>>(pairs, pairs_alt, row_tile_offset, 6145, 12289, capacity);
-    tile_sort_kernel<512, true><<<n_buckets, 512, sizeof(SortShared<512>), st>>>(pairs, pairs_alt, row_tile_offset, 12289, 0x7fffffff,
-                                                                               capacity);
+cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
+                                 long long capacity, cudaStream_t st, int *n_launches) {
+    // grid = SMs x resident CTAs of the class (threads / shared memory bound)
+    const int sms = g_sort_sms;
+    tile_sort_kernel<128, false><<<sms * 16, 128, sort_smem<128>(SAS_SORT_CAP0), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 0,
+                                                                                     SAS_SORT_CAP0, capacity);
+    tile_sort_kernel<256, false><<<sms * 5, 256, sort_smem<256>(SAS_SORT_CAP1), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 1,
+                                                                                    SAS_SORT_CAP1, capacity);
+    tile_sort_kernel<512, false><<<sms * 2, 512, sort_smem<512>(SAS_SORT_CAP2), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 2,
+                                                                                    SAS_SORT_CAP2, capacity);
+    tile_sort_kernel<512, false><<<sms, 512, sort_smem<512>(SAS_SORT_CAP3), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 3,
+                                                                                SAS_SORT_CAP3, capacity);
+    tile_sort_kernel<512, true><<<sms, 512, sizeof(SortShared<512>), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0, capacity);
     if (n_launches) *n_launches += 5;
     return cudaGetLastError();
 }

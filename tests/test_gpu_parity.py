@@ -185,7 +185,7 @@ def test_overflow_is_reported_and_regrown():
     r.set_cameras(vm, S.fov_intrinsics(W, H), W, H)
     r.render(("rgb",), check=False)
     st = r.stats()
-    assert st["overflow"] == 1 and st["n_isects"] > 2000
+    assert st["overflow"] != 0 and st["n_isects"] > 2000
     out = r.render(("rgb", "depth", "alpha", "rgb_u8", "n_contrib"), check=True)  # grows and re-renders
     assert r.stats()["overflow"] == 0
     ref = oracle.render(sc.as_oracle_dict(), vm, S.fov_intrinsics(W, H)[None], W, H)
