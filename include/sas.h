@@ -142,11 +142,13 @@ int sas_get_stats(sas_renderer *r, sas_stats *out);
 
 /* Intermediates of the last render, for parity tests (synchronises). */
 #define SAS_DBG_RECORDS 1   /* [C*n_bg + I*(N-n_bg), 12] f32: per view the background records, then per image the link
-                               records: m2x,m2y,0.5*conic_a,conic_b, 0.5*conic_c,opacity,radius_x,radius_y, r,g,b,depth */
+                               records: m2x,m2y,0.5*conic_a,conic_b, 0.5*conic_c,opacity,extent_x,extent_y, r,g,b,depth
+                               (extent = conservative screen-space reach of alpha >= 1/255, used only for culling) */
 #define SAS_DBG_BINS 2      /* same rows, [.,2] u32: (x0 | y0<<8 | x1<<16 | y1<<24), bits(depth); tile rect, exclusive max */
 #define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of the merged per-(image,tile) counts = gsplat isect_offsets */
 #define SAS_DBG_SORTED_GIDS 4  /* [M] i32 canonical Gaussian index per intersection, (image,tile,depth,gid) order */
 #define SAS_DBG_VIEW_OF_IMAGE 5 /* [I] i32 */
+#define SAS_DBG_RADII 6     /* same rows as the records, u32: radius_x | radius_y << 16 (gsplat radii; undefined where culled) */
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
 
 /* Per-stage device timing (CUDA events on the caller's stream around each stage of sas_render).

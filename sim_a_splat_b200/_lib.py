@@ -19,6 +19,7 @@ SAS_DBG_BINS = 2
 SAS_DBG_TILE_OFFSETS = 3
 SAS_DBG_SORTED_GIDS = 4
 SAS_DBG_VIEW_OF_IMAGE = 5
+SAS_DBG_RADII = 6
 
 EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",

@@ -42,7 +42,7 @@ struct sas_renderer {
     bool cameras_set = false;
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
-    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc;
+    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii;
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -159,6 +159,7 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
     SAS_CUDA_C(sas_sort_init(n_sms));
     SAS_CUDA_C(sas_composite_init(n_sms));
+    SAS_CUDA_C(sas_bin_init());
 
     // bring the scene to the host if needed, pack SoA, upload
     std::vector<float> h_means((size_t)N * 3), h_quats((size_t)N * 4), h_scales((size_t)N * 3), h_op(N), h_sh((size_t)N * K * 3);
@@ -230,7 +231,7 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc,
-                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc};
+                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -309,6 +310,7 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     int rc;
     if ((rc = ensure(r, r->rec, n_rec * sizeof(SasRecord)))) return rc;
     if ((rc = ensure(r, r->bins, n_rec * sizeof(uint2)))) return rc;
+    if ((rc = ensure(r, r->radii, n_rec * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_count, RT * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_cursor, RT * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_offset, (RT + 1) * 4))) return rc;
@@ -371,7 +373,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
         SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
-                                       r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, rcount,
+                                       r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (unsigned *)r->radii.p, rcount,
                                        r->counters, st));
         launches += 1;
     }
@@ -467,6 +469,7 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
     switch (what) {
         case SAS_DBG_RECORDS: src = r->rec.p; avail = n_rec * sizeof(SasRecord); break;
         case SAS_DBG_BINS: src = r->bins.p; avail = n_rec * sizeof(uint2); break;
+        case SAS_DBG_RADII: src = r->radii.p; avail = n_rec * 4; break;
         case SAS_DBG_TILE_OFFSETS: src = r->img_tile_offset.p; avail = (IT + 1) * 4; break;
         case SAS_DBG_VIEW_OF_IMAGE: src = r->view_of_image; avail = (size_t)r->I * 4; break;
         case SAS_DBG_SORTED_GIDS: {

@@ -105,6 +105,9 @@ struct SasRowSpan {
 #define SAS_SORT_CAP2 5632
 #define SAS_SORT_CAP3 12288
 #define SAS_COMP_CLASSES 32
+// Images with at most this many tiles count / reserve bucket slots through per-CTA shared-memory
+// histograms (projection and emission); larger images fall back to global atomics per intersection.
+#define SAS_SMEM_TILES_MAX 8192
 
 // Device-side work lists of one render call (sas_work.cu); zeroed with the counters.
 struct SasWork {
@@ -132,7 +135,8 @@ cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int 
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st);
+                               unsigned int *radii_out, unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st);
+cudaError_t sas_bin_init();
 cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,
                             unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,

@@ -13,14 +13,15 @@
 // with three 16 B cp.async copies (double buffered, the id for the batch after next prefetched into
 // a register), so global latency overlaps the arithmetic of the current batch.  Inside a batch each
 // warp first tests 32 Gaussians at once (one per lane) against its footprint using the record's
-// screen-space radii, ballots the hits, and only walks the set bits -- in order, so front-to-back
+// screen-space extents, ballots the hits, and only walks the set bits -- in order, so front-to-back
 // order is preserved.  A lane stops when T*(1-alpha) <= 1e-4; a warp skips once all its lanes
 // stopped; the CTA leaves the tile when __syncthreads_count says all 256 pixels stopped.
 //
-// The footprint test is conservative: a pixel outside a Gaussian's radius box has
-// sigma > 0.5*3.33^2 = 5.544 > ln(255), i.e. alpha < 1/255 for any opacity <= 1, so the reference
-// rule would have skipped it as well (one extra pixel of slack absorbs rounding).  Likewise
-// sigma > SAS_SIGMA_SKIP skips the exp.  Neither changes any output bit.
+// The footprint test is conservative: the extents (sas_project.cu) bound the region where
+// alpha >= 1/255 is possible -- a pixel with |dx| > ex has sigma >= dx^2/(2 cov_xx) > ln(255*opacity),
+// i.e. alpha < 1/255, so the reference rule would have skipped it as well (the extents carry a
+// margin far above the rounding of sigma).  Likewise sigma > SAS_SIGMA_SKIP skips the exp.  Neither
+// changes any output bit.
 //
 // Not bandwidth bound: FP32 issue bound (sigma, the polynomial exp, 4 FMA accumulations).
 // (An mbarrier ring that let warps drift 1-2 batches apart instead of meeting at a barrier every
@@ -41,7 +42,7 @@ __device__ __forceinline__ unsigned char to_u8(float v) {
 
 struct Pixel {
     float pxf, pyf;            // pixel centre
-    float bx0, bx1, by0, by1;  // footprint bounds (pixel centres, +-1 px slack)
+    float bx0, bx1, by0, by1;  // footprint bounds (first / last pixel centre of the warp's 8x4 block)
     float T, ar, ag, ab, ad;   // transmittance and accumulators
     int nc;
     bool done;
@@ -163,8 +164,8 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         const bool inside = (px < W) && (py < H);
         Pixel p;
         p.pxf = (float)px + 0.5f; p.pyf = (float)py + 0.5f;
-        p.bx0 = (float)fx + 0.5f - 1.0f; p.bx1 = (float)fx + 7.5f + 1.0f;
-        p.by0 = (float)fy + 0.5f - 1.0f; p.by1 = (float)fy + 3.5f + 1.0f;
+        p.bx0 = (float)fx + 0.5f; p.bx1 = (float)fx + 7.5f;
+        p.by0 = (float)fy + 0.5f; p.by1 = (float)fy + 3.5f;
         p.T = 1.0f; p.ar = p.ag = p.ab = p.ad = 0.0f;
         p.nc = 0;
         p.done = !inside;

@@ -43,20 +43,14 @@ __device__ __forceinline__ void sh_bases(int deg, float x, float y, float z, flo
     b[15] = fTmpA * fC2; b[9] = fTmpA * fS2;
 }
 
-// One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
-// cameras), the link span once per IMAGE (rows = env x camera) -- see sas_common.cuh.
-template <int DEG, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS)
-project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
-               const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
-               const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
-               uint2 *__restrict__ bins, unsigned int *__restrict__ row_tile_count, SasCounters *counters) {
-    const int local = blockIdx.x * 256 + threadIdx.x;
-    const int row = blockIdx.y;
-    if (local >= span.n) return;
-    const int g = span.g0 + local;
-    const size_t ig = (size_t)span.rec0 + (size_t)row * span.n + local;
-    const SasCamera *cam = row_cams + span.row0 + row;
+// Projects Gaussian g for one row (camera [+ env]); writes its bin and, if visible, its record and
+// radii.  Returns visibility and the tile rectangle.
+template <int DEG>
+__device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat,
+                                            const float4 *__restrict__ scale_link, const float *__restrict__ sh_planes, int n_pad, int g,
+                                            size_t ig, const float *__restrict__ link_poses, int L, const SasCamera *__restrict__ cam, int W,
+                                            int H, int tile_w, int tile_h, SasRecord *__restrict__ rec, uint2 *__restrict__ bins,
+                                            unsigned int *__restrict__ radii_out, int &x0, int &y0, int &x1, int &y1) {
 
     const float4 mo = __ldg(mean_op + g);
     const float4 qq = __ldg(quat + g);
@@ -164,17 +158,18 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
     }
     if (!vis) {
         bins[ig] = make_uint2(0u, 0u);
-        return;
+        return false;
     }
 
     // S4: tile rectangle (gsplat _isect_tiles)
     const float tmx = m2x / (float)SAS_TILE_PX, tmy = m2y / (float)SAS_TILE_PX;
     const float trx = rx / (float)SAS_TILE_PX, try_ = ry / (float)SAS_TILE_PX;
-    int x0 = (int)floorf(tmx - trx), y0 = (int)floorf(tmy - try_);
-    int x1 = (int)ceilf(tmx + trx), y1 = (int)ceilf(tmy + try_);
+    x0 = (int)floorf(tmx - trx); y0 = (int)floorf(tmy - try_);
+    x1 = (int)ceilf(tmx + trx); y1 = (int)ceilf(tmy + try_);
     x0 = min(max(x0, 0), tile_w); x1 = min(max(x1, 0), tile_w);
     y0 = min(max(y0, 0), tile_h); y1 = min(max(y1, 0), tile_h);
     bins[ig] = make_uint2((unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24), __float_as_uint(czm));
+    radii_out[ig] = (unsigned)fminf(rx, 65535.0f) | ((unsigned)fminf(ry, 65535.0f) << 16);
 
     // S3: SH colour, view direction rotated into the link's rest frame
     float dx = mx - cam->campos[0], dy = my - cam->campos[1], dz = mz - cam->campos[2];
@@ -200,19 +195,66 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
         col[ch] = fmaxf(acc + 0.5f, 0.0f);
     }
 
+    // Screen-space extent the compositor culls with: a pixel can pass alpha >= 1/255 only if
+    // sigma <= tau = ln(255*opacity), and sigma >= dx^2/(2a) (a = blurred cov_xx), so |dx| <= sqrt(2*tau*a).
+    // Not part of the numerics contract (it only skips work): logf is the device libm, and the bound
+    // carries a margin (tau + 0.01, x1.001, + 0.02 px) far above the rounding of sigma; it never exceeds
+    // the gsplat radius + 1.
+    const float tau = fmaxf(logf(255.0f * mo.w) + 0.01f, 0.0f);
+    const float ex = fminf(sqrtf(2.0f * tau * a) * 1.001f + 0.02f, rx + 1.0f);
+    const float ey = fminf(sqrtf(2.0f * tau * c) * 1.001f + 0.02f, ry + 1.0f);
+
     SasRecord r;
     r.a = make_float4(m2x, m2y, 0.5f * (c / det), -b / det);
-    r.b = make_float4(0.5f * (a / det), mo.w, rx, ry);
+    r.b = make_float4(0.5f * (a / det), mo.w, ex, ey);
     r.c = make_float4(col[0], col[1], col[2], czm);
     rec[ig] = r;
+    return true;
+}
 
-    // per-(row,tile) counts; their exclusive scan gives the bucket offsets
-    unsigned int *tc = row_tile_count + (size_t)(span.row0 + row) * tile_w * tile_h;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) atomicAdd(tc + y * tile_w + x, 1u);
+constexpr int PROJ_FAST_TILES = 4;  // Gaussians covering at most this many tiles count through shared memory
+
+// One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
+// cameras), the link span once per IMAGE (rows = env x camera) -- see sas_common.cuh.  Per-(row,tile)
+// counts are accumulated in shared memory per CTA (one global RED per touched tile per CTA instead
+// of one per intersection); Gaussians covering many tiles, and images with more tiles than fit in
+// shared memory, add to the global counters directly.
+template <int DEG, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
+project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
+               const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
+               const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
+               uint2 *__restrict__ bins, unsigned int *__restrict__ radii_out, unsigned int *__restrict__ row_tile_count,
+               SasCounters *counters, int smem_tiles) {
+    extern __shared__ unsigned int s_cnt[];  // [smem_tiles] (0 = direct global counting)
+    const int T = tile_w * tile_h;
+    for (int t = threadIdx.x; t < smem_tiles; t += 256) s_cnt[t] = 0u;
+    if (smem_tiles) __syncthreads();
+
+    const int local = blockIdx.x * 256 + threadIdx.x;
+    const int row = blockIdx.y;
+    bool vis = false;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (local < span.n)
+        vis = project_one<DEG>(mean_op, quat, scale_link, sh_planes, n_pad, span.g0 + local,
+                               (size_t)span.rec0 + (size_t)row * span.n + local, link_poses, L, row_cams + span.row0 + row, W, H, tile_w,
+                               tile_h, rec, bins, radii_out, x0, y0, x1, y1);
+    unsigned int *tc = row_tile_count + (size_t)(span.row0 + row) * T;
+    if (vis) {
+        const bool fast = smem_tiles && (x1 - x0) * (y1 - y0) <= PROJ_FAST_TILES;
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) atomicAdd((fast ? s_cnt : tc) + y * tile_w + x, 1u);
+    }
     {  // one counter update per warp instead of one per thread
-        const unsigned m = __activemask();
-        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&counters->n_visible_src, (unsigned long long)__popc(m));
+        const unsigned m = __ballot_sync(0xffffffffu, vis);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters->n_visible_src, (unsigned long long)__popc(m));
+    }
+    if (smem_tiles) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < smem_tiles; t += 256) {
+            const unsigned c = s_cnt[t];
+            if (c) atomicAdd(tc + t, c);
+        }
     }
 }
 
@@ -221,24 +263,25 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st) {
+                               unsigned int *radii_out, unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st) {
     if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
     dim3 grid((span.n + 255) / 256, span.rows);
-    // SAS_PROJECT=1 (environment, read once): registers uncapped at 2 CTAs/SM so all SH loads of a thread are in
-    // flight at once; default 0 = 3-4 CTAs/SM.
+    const int T = tile_w * tile_h;
+    const int smem_tiles = T <= SAS_SMEM_TILES_MAX ? T : 0;
+    const size_t smem = (size_t)smem_tiles * sizeof(unsigned int);
+    // SAS_PROJECT=n (environment, read once): minimum resident CTAs/SM the register allocation targets (3, 4 or 5).
     static int variant = -1;
     if (variant < 0) {
         const char *e = getenv("SAS_PROJECT");
-        variant = (e && atoi(e) == 1) ? 1 : 0;
+        variant = e ? atoi(e) : 4;
+        if (variant < 3 || variant > 5) variant = 4;
     }
-#define SAS_PROJ(D)                                                                                                                   \
-    do {                                                                                                                              \
-        if (variant == 1)                                                                                                             \
-            project_kernel<D, 2><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, \
-                                                      H, tile_w, tile_h, rec, bins, row_tile_count, counters);                        \
-        else                                                                                                                          \
-            project_kernel<D, 3><<<grid, 256, 0, st>>>(mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, \
-                                                      H, tile_w, tile_h, rec, bins, row_tile_count, counters);                        \
+#define SAS_PROJ_ARGS mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, H, tile_w, tile_h, rec, bins, radii_out,                       row_tile_count, counters, smem_tiles
+#define SAS_PROJ(D)                                                                              \
+    do {                                                                                         \
+        if (variant == 3) project_kernel<D, 3><<<grid, 256, smem, st>>>(SAS_PROJ_ARGS);          \
+        else if (variant == 5) project_kernel<D, 5><<<grid, 256, smem, st>>>(SAS_PROJ_ARGS);     \
+        else project_kernel<D, 4><<<grid, 256, smem, st>>>(SAS_PROJ_ARGS);                       \
     } while (0)
     switch (sh_degree) {
         case 0: SAS_PROJ(0); break;
@@ -247,5 +290,6 @@ cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const 
         default: SAS_PROJ(3); break;
     }
 #undef SAS_PROJ
+#undef SAS_PROJ_ARGS
     return cudaGetLastError();
 }

@@ -180,10 +180,11 @@ class SplatRenderer:
         n_rec = C * nbg + I * ndy
         rec_raw = np.empty((n_rec, 12), dtype=np.float32)
         bins_raw = np.empty((n_rec, 2), dtype=np.uint32)
+        radii_raw = np.empty((n_rec, 1), dtype=np.uint32)
         offs = np.empty(I * T + 1, dtype=np.int32)
         gids = np.empty(M, dtype=np.int32)
         voi = np.empty(I, dtype=np.int32)
-        for what, arr in ((L.SAS_DBG_RECORDS, rec_raw), (L.SAS_DBG_BINS, bins_raw), (L.SAS_DBG_TILE_OFFSETS, offs),
+        for what, arr in ((L.SAS_DBG_RECORDS, rec_raw), (L.SAS_DBG_BINS, bins_raw), (L.SAS_DBG_RADII, radii_raw), (L.SAS_DBG_TILE_OFFSETS, offs),
                           (L.SAS_DBG_SORTED_GIDS, gids), (L.SAS_DBG_VIEW_OF_IMAGE, voi)):
             L.check(self._lib, self._h, self._lib.sas_debug_fetch(self._h, what, arr.ctypes.data, arr.nbytes))
 
@@ -192,7 +193,8 @@ class SplatRenderer:
             dy = raw[C * nbg:].reshape(I, ndy, raw.shape[1])
             return np.concatenate([bg, dy], axis=1)
 
-        rec, bins = per_image(rec_raw), per_image(bins_raw)
+        rec, bins, rad = per_image(rec_raw), per_image(bins_raw), per_image(radii_raw)[..., 0]
+        radii = np.stack([rad & 0xffff, rad >> 16], axis=-1).astype(np.int32)
         rect = np.stack([bins[..., 0] & 0xff, (bins[..., 0] >> 8) & 0xff, (bins[..., 0] >> 16) & 0xff, bins[..., 0] >> 24], axis=-1).astype(np.int32)
         vis = bins[..., 0] != 0
         tiles = ((rect[..., 2] - rect[..., 0]) * (rect[..., 3] - rect[..., 1])).astype(np.int32)
@@ -208,7 +210,7 @@ class SplatRenderer:
         depth_bits = bins.reshape(-1, 2)[flat, 1].astype(np.int64)
         isect_ids = (img << (32 + tile_bits)) | (tile << 32) | depth_bits
         return dict(
-            radii=z(rec[..., 6:8]).astype(np.int32), means2d=z(rec[..., 0:2]), depths=z(rec[..., 11]), conics=z(conics),
+            radii=z(radii), extents=z(rec[..., 6:8]), means2d=z(rec[..., 0:2]), depths=z(rec[..., 11]), conics=z(conics),
             colors=z(rec[..., 8:11]), opacities=z(rec[..., 5]), tiles_per_gauss=z(tiles), tile_rect=z(rect), visible=vis,
             isect_ids=isect_ids, flatten_ids=flat.astype(np.int32), isect_offsets=offs[:-1].reshape(I, th, tw).copy(),
             M=M, tile_bits=tile_bits, stats=s, view_of_image=voi,

@@ -38,7 +38,7 @@ def test_sass_is_sm100a_and_uses_async_copies():
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", str(_build.LIB)], capture_output=True, text=True).stdout
     assert "LDGSTS" in sass  # cp.async staging in the compositor
-    assert "MATCH.ANY" in sass  # warp multi-split in the bucket sort
+    assert "VOTE" in sass and "ATOMS" in sass  # ballot multi-split / shared-memory histograms in the bucket sort
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
