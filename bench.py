@@ -49,45 +49,56 @@ def build_workload(rank: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line), through NVML
+    (same counters nvidia-smi prints; a subprocess per sample is too slow for a sub-second region)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device: int):
-        self.device, self.rows, self._stop, self._t = device, [], threading.Event(), None
+        self.device, self.sm, self.mask, self._stop, self._t, self.max_mhz, self.power = device, [], 0, threading.Event(), None, None, []
+        try:
+            import pynvml
 
-    def _run(self):
-        while not self._stop.is_set():
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                import torch
+
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=2)
 
     def summary(self) -> dict:
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active") and not v.lower().startswith("not"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "source": "NVML, 5 ms period, sampled inside the timed region"}
 
 
 def algorithmic_bytes(st: dict, N: int, K_sh: int, out_bytes_per_px: int) -> dict:
@@ -216,6 +227,8 @@ def run_ours(args):
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm = float(peaks.get("hbm_gbs", 6650.0))
+        tj = ROOT / "profiles" / "traffic.json"
+        traffic = json.loads(tj.read_text()) if tj.exists() else {}
         dom = max((k for k in ab), key=lambda k: stage[k])
         stages = {k: {"ms": round(stage[k], 4), "alg_bytes": int(ab[k]) if k in ab else None,
                       "gbs": round(ab[k] / (stage[k] * 1e-3) / 1e9, 1) if k in ab and stage[k] > 0 else None} for k in stage}
@@ -232,7 +245,8 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ab[dom] / (stage[dom] * 1e-3) / 1e9, 1), "peak": hbm,
-                         "unit": "GB/s", "frac": round(ab[dom] / (stage[dom] * 1e-3) / 1e9 / hbm, 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(ab[dom] / (stage[dom] * 1e-3) / 1e9 / hbm, 4), "traffic": traffic.get(dom),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this command (profiles/traffic.json)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "the compositor is FP32-issue bound, not HBM bound (DESIGN.md); its GB/s is reported for the contract, "
                                  "see fp32 and stages for the numbers that explain it"},
@@ -307,11 +321,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 200; 20 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 200
     if args.impl == "reference":
         run_reference(args)
     else:

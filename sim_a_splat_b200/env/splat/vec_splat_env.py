@@ -1,0 +1,72 @@
+"""Batched observation rendering for E parallel envs -- the extension BASELINE.json asks for on top of the
+reference's single-env wrapper (the reference renders one camera of one env per browser round trip,
+/root/reference/sim_a_splat/env/splat/splat_env_wrapper.py:147-158).
+
+One `VecSplatRenderer.render(draw_msgs)` call = one pass of the hot path over E x C images: the per-env link
+poses come from `SplatHandler.link_poses_from_msg` (the draw_handler algebra), fixed cameras are shared
+views, link-attached cameras get one view per env.  Observations keep the reference layout: `camera_{i}`
+= uint8 [E,3,H,W] (splat_env_wrapper.py:132-138).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from ...renderer import SplatRenderer
+from ...scene import c2w_opencv_to_viewmat
+from ...splat.splat_handler import SplatHandler
+
+
+class VecSplatRenderer:
+    def __init__(self, handler: SplatHandler, camera_setup_info: dict, n_envs: int, fov: float = np.radians(75.0),
+                 background=(1.0, 1.0, 1.0), device: int = 0, max_isects: int = 0, env_range: Optional[range] = None):
+        """env_range: the envs this process renders (multi-GPU sharding, see sim_a_splat_b200/dist.py)."""
+        self.handler, self.info, self.fov, self.background = handler, camera_setup_info, fov, background
+        self.envs = list(env_range) if env_range is not None else list(range(n_envs))
+        self.moving = {k: v for k, v in camera_setup_info.items() if v.get("type") == "moving"}
+        self.fixed = {k: v for k, v in camera_setup_info.items() if v.get("type") in ("viewport", "static")}
+        self.keys = list(self.moving.keys()) + list(self.fixed.keys())  # reference order: moving first (:53-55)
+        sizes = {tuple(camera_setup_info[k]["render_size"][:2]) for k in self.keys}
+        if len(sizes) != 1:
+            raise ValueError("VecSplatRenderer renders one image size per call; group cameras by render_size")
+        self.H, self.W = (int(v) for v in sizes.pop())
+        scene = handler.server.build_scene()
+        self.E, self.C = len(self.envs), len(self.keys)
+        self.renderer = SplatRenderer(scene, device=device, max_images=self.E * self.C, max_envs=self.E, max_width=self.W,
+                                      max_height=self.H, max_isects=max_isects)
+        fy = self.H / (2.0 * np.tan(fov / 2.0))
+        self.K = np.array([[fy, 0, self.W / 2.0], [0, fy, self.H / 2.0], [0, 0, 1.0]])
+        self._fixed_vm = [c2w_opencv_to_viewmat(v["local_frame"].rotation().wxyz, v["local_frame"].translation()) for v in self.fixed.values()]
+        self._static_cameras_set = False
+
+    def render(self, draw_msgs: Sequence, outputs=("rgb_u8",), to_host: bool = True) -> Dict[str, np.ndarray]:
+        assert len(draw_msgs) == self.E
+        poses = np.stack([self.handler.link_poses_from_msg(m) for m in draw_msgs])  # [E,L,12]
+        r = self.renderer
+        r.set_link_poses(poses)
+        if self.moving or not self._static_cameras_set:
+            vms, env = [], []
+            for e, msg in enumerate(draw_msgs):
+                for info in self.moving.values():
+                    wxyz, xyz = self.handler.get_attached_frame(info["link_name"], info["local_frame"], msg)
+                    vms.append(c2w_opencv_to_viewmat(wxyz, xyz))
+                vms += self._fixed_vm
+                env += [e] * self.C
+            r.set_cameras(np.stack(vms), self.K, self.W, self.H, np.asarray(env, dtype=np.int32))
+            self._static_cameras_set = True
+        out = r.render(outputs, background=self.background, to_host=to_host)
+        res = {}
+        for name, t in out.items():
+            a = t.numpy() if to_host else t
+            a = a.reshape(self.E, self.C, *a.shape[1:])
+            for ci in range(self.C):
+                img = a[:, ci]
+                if name == "rgb_u8":
+                    res[f"camera_{ci}"] = np.moveaxis(img, -1, 1) if to_host else img.permute(0, 3, 1, 2)
+                else:
+                    res[f"{name}_{ci}"] = img
+        return res
+
+    def close(self):
+        self.renderer.close()
