@@ -6,6 +6,7 @@
 #include "sas_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,7 +43,9 @@ struct sas_renderer {
     bool cameras_set = false;
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
-    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii;
+    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask;
+    cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
+    cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -120,6 +123,15 @@ void fill_camera(SasCamera &c, const float *vm, const float *K, int width, int h
 }
 
 }  // namespace
+
+int sas_variant_flags() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SAS_VARIANT");
+        v = e ? (int)strtol(e, nullptr, 0) & 0xff : 0xff;
+    }
+    return v;
+}
 
 extern "C" {
 
@@ -209,6 +221,8 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     r->stage_bytes = sizeof(SasCamera) * 2 * cfg->max_images + sizeof(int) * cfg->max_images;
     SAS_CUDA_C(cudaMallocHost(&r->stage_host, r->stage_bytes));
     SAS_CUDA_C(cudaEventCreateWithFlags(&r->cams_copied, cudaEventDisableTiming));
+    for (cudaStream_t &s : r->aux) SAS_CUDA_C(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (cudaEvent_t &ev : r->fork_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
     long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
@@ -229,9 +243,13 @@ void sas_destroy(sas_renderer *r) {
     if (r->cams_copied) cudaEventDestroy(r->cams_copied);
     for (cudaEvent_t ev : r->stage_ev)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : r->fork_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t s : r->aux)
+        if (s) cudaStreamDestroy(s);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc,
-                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii};
+                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -317,6 +335,7 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     if ((rc = ensure(r, r->img_tile_offset, (IT + 1) * 4))) return rc;
     if ((rc = ensure(r, r->block_sums, (RT / 1024 + 2) * 4))) return rc;
     if ((rc = ensure(r, r->img_max, (size_t)n_images * 4))) return rc;
+    if ((rc = ensure(r, r->dyn_mask, IT * 4))) return rc;
     // work lists (sas_work.cu) and the per-view tile buffers shared by the images of a view
     const size_t VT = (size_t)C * T, VP = (size_t)C * width * height;
     if ((rc = ensure(r, r->sort_list, RT * 4))) return rc;
@@ -357,6 +376,9 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
 
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_count.p, 0, RT * 4, st));
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_cursor.p, 0, RT * 4, st));
+    // group reach masks (sas_common.cuh): OR-ed by the link projection; all-ones = "composite every group"
+    SAS_CUDA(r, cudaMemsetAsync(r->dyn_mask.p, (sas_variant_flags() & 2) ? 0 : 0xff, IT * 4, st));
+    unsigned *dyn_mask = (unsigned *)r->dyn_mask.p;
     SAS_CUDA(r, cudaMemsetAsync(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork), st));  // counters and work lists
     SasWork *work = reinterpret_cast<SasWork *>(r->counters + 1);
 
@@ -374,15 +396,15 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         if (sp.n <= 0) continue;
         SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
                                        r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (unsigned *)r->radii.p, rcount,
-                                       r->counters, st));
+                                       sp.row0 == C ? dyn_mask : nullptr, r->counters, st));
         launches += 1;
     }
     SAS_STAGE(1);
     SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st, &launches));
     SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
                                 &launches));
-    SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, C, I, T, work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p,
-                                      (int *)r->comp_list.p, st, &launches));
+    SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, work, (unsigned char *)r->view_needed.p,
+                                      (int *)r->sort_list.p, (int *)r->comp_list.p, st, &launches));
     SAS_STAGE(2);
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
@@ -390,16 +412,18 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         launches += 1;
     }
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, &launches));
-    SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects, st));
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, r->aux, r->fork_ev,
+                                     &launches));
+    SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects,
+                                 (sas_variant_flags() & 8) ? 0 : 1, st));
     launches += 1;
     SAS_STAGE(4);
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
     const SasOutputs img_out{d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc};
     const SasViewBuf view_out{(float *)r->v_acc.p, (float *)r->v_depth.p, (int *)r->v_nc.p};
-    SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, (const int *)r->comp_list.p, work, r->n_bg,
-                                     r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, r->max_isects, r->max_isects,
+    SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, dyn_mask, (const int *)r->comp_list.p, work,
+                                     r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, r->max_isects, r->max_isects,
                                      r->counters, st, &launches));
     SAS_STAGE(5);
     if (ns) {
@@ -476,6 +500,11 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
             SasCounters c;
             SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
             long long m = (long long)c.n_isects < r->max_isects ? (long long)c.n_isects : r->max_isects;
+            // the render skips the id lists of tiles without link Gaussians (the compositor takes those from the
+            // view's bucket); produce them now
+            SAS_CUDA(r, sas_launch_merge((const uint2 *)r->pairs.p, (const int *)r->row_tile_offset.p, (const int *)r->img_tile_offset.p,
+                                         r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects, r->max_isects, 1, 0));
+            SAS_CUDA(r, cudaDeviceSynchronize());
             src = r->merged.p; avail = (size_t)m * 4;
             break;
         }

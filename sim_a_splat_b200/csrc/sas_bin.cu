@@ -178,16 +178,38 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bin
 }
 
 // K5: merged[image,tile] = stable merge of the view's sorted background bucket and the image's
-// sorted link bucket, by depth bits, background first on ties.  Rank-based: every element finds
-// its output slot with one binary search in the other list (the link list's keys are staged in
-// shared memory, it is the short one).
+// sorted link bucket, by depth bits, background first on ties (background ids are the lower ones in
+// canonical order, so this is the order a stable sort of gsplat's keys gives).
+//
+// Merge-path: one CTA per (image, tile).  The output is cut into chunks of 1024 ids; the split of
+// every chunk boundary (how many background entries precede it) is found up front by one thread per
+// boundary with a binary search over the two global lists; per chunk the two key/id windows are
+// staged in shared memory, every thread finds the split of its own 8-id diagonal with a search in
+// shared memory and merges 8 ids sequentially, writing 32 contiguous bytes.  Tiles whose link
+// bucket is empty are skipped (the compositor takes them from the view's bucket) unless fill_static.
 constexpr int MERGE_THREADS = 128;
-constexpr int MERGE_SMEM_KEYS = 2048;
+constexpr int MERGE_VT = 8;
+constexpr int MERGE_CHUNK = MERGE_THREADS * MERGE_VT;
+constexpr int MERGE_MAX_SPLITS = 64;  // chunk boundaries resolved per round
+
+// number of background entries among the first d merged entries
+template <typename KA, typename KB>
+__device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB key_b) {
+    int lo = max(0, d - nb), hi = min(d, na);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key_a(mid) <= key_b(d - 1 - mid)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                               const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
-                                                              int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all) {
-    __shared__ unsigned dkeys[MERGE_SMEM_KEYS];
+                                                              int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all,
+                                                              int fill_static) {
+    __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
+    __shared__ int s_out[MERGE_CHUNK];
+    __shared__ int s_split[MERGE_MAX_SPLITS + 1];
     const int t = blockIdx.x, i = blockIdx.y;
     const size_t bb = (size_t)view_of_image[i] * T + t, db = (size_t)(C + i) * T + t;
     long long b0 = row_tile_offset[bb], b1 = row_tile_offset[bb + 1];
@@ -196,46 +218,52 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
     if (b0 < 0 || b1 < b0 || d0 < 0 || d1 < d0 || o0 < 0) return;
     if (b1 > cap_src) b1 = cap_src;
     if (d1 > cap_src) d1 = cap_src;
-    const int nb = b1 > b0 ? (int)(b1 - b0) : 0, nd = d1 > d0 ? (int)(d1 - d0) : 0;
+    const int na = b1 > b0 ? (int)(b1 - b0) : 0, nb = d1 > d0 ? (int)(d1 - d0) : 0;
+    if (nb == 0 && !fill_static) return;  // composited from the view's bucket; ids only needed by debug fetches
     const uint2 *bgp = pairs + b0, *dyp = pairs + d0;
-    if (nd == 0 || nb == 0) {  // only one list (a static tile, or no background here): plain copy
-        const uint2 *src = nd == 0 ? bgp : dyp;
-        const int n = nd == 0 ? nb : nd;
+    const int n = na + nb;
+    if (nb == 0 || na == 0) {  // only one list (a static tile, or no background here): plain copy
+        const uint2 *src = nb == 0 ? bgp : dyp;
         for (int k = threadIdx.x; k < n; k += MERGE_THREADS) {
             const long long pos = o0 + k;
             if (pos < cap_all) merged[pos] = (int)src[k].y;
         }
         return;
     }
-    const bool staged = nd <= MERGE_SMEM_KEYS;
-    if (staged)
-        for (int j = threadIdx.x; j < nd; j += MERGE_THREADS) dkeys[j] = dyp[j].x;
-    __syncthreads();
-    // lower(key) = number of link entries strictly nearer than a background entry with that key
-    auto lower = [&](unsigned key) {
-        int lo = 0, hi = nd;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const unsigned dk = staged ? dkeys[mid] : dyp[mid].x;
-            if (dk < key) lo = mid + 1; else hi = mid;
+    const int n_chunks = (n + MERGE_CHUNK - 1) / MERGE_CHUNK;
+    for (int cr = 0; cr < n_chunks; cr += MERGE_MAX_SPLITS) {  // rounds of up to MERGE_MAX_SPLITS chunks
+        __syncthreads();
+        if (threadIdx.x <= MERGE_MAX_SPLITS && cr + (int)threadIdx.x <= n_chunks) {
+            const int d = min(n, (cr + (int)threadIdx.x) * MERGE_CHUNK);
+            s_split[threadIdx.x] = merge_path(d, na, nb, [&](int k) { return __ldg(&bgp[k].x); }, [&](int k) { return __ldg(&dyp[k].x); });
         }
-        return lo;
-    };
-    // Background entry k lands at k + lower(k).  Link entry j lands at j + (number of background
-    // entries with key <= its key) = j + (first k with lower(k) > j): the background thread whose
-    // lower() steps past j writes it, so no search over the long background list is needed.
-    for (int k = threadIdx.x; k <= nb; k += MERGE_THREADS) {
-        const int lo_prev = k > 0 ? lower(bgp[k - 1].x) : 0;
-        int lo_k = nd;
-        if (k < nb) {
-            const uint2 p = bgp[k];
-            lo_k = lower(p.x);
-            const long long pos = o0 + k + lo_k;
-            if (pos < cap_all) merged[pos] = (int)p.y;
-        }
-        for (int j = lo_prev; j < lo_k; j++) {  // link entries between background k-1 and k (k = nb: the tail)
-            const long long pos = o0 + j + k;
-            if (pos < cap_all) merged[pos] = (int)dyp[j].y;
+        __syncthreads();
+        const int c_end = min(n_chunks, cr + MERGE_MAX_SPLITS);
+        for (int c = cr; c < c_end; c++) {
+            const int c0 = c * MERGE_CHUNK, cn = min(MERGE_CHUNK, n - c0);
+            const int a0 = s_split[c - cr], a1 = s_split[c - cr + 1];
+            const int wa = a1 - a0, wb = cn - wa, bst = c0 - a0;
+            for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sa[k] = bgp[a0 + k];
+            for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[bst + k];
+            __syncthreads();
+            const int d = threadIdx.x * MERGE_VT;
+            if (d < cn) {
+                int ia = merge_path(d, wa, wb, [&](int k) { return sa[k].x; }, [&](int k) { return sb[k].x; });
+                int ib = d - ia;
+#pragma unroll
+                for (int v = 0; v < MERGE_VT; v++) {
+                    if (d + v < cn) {
+                        const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
+                        s_out[d + v] = (int)(take_a ? sa[ia].y : sb[ib].y);
+                        if (take_a) ia++; else ib++;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < cn; k += MERGE_THREADS) {  // coalesced write-out
+                const long long pos = o0 + c0 + k;
+                if (pos < cap_all) merged[pos] = s_out[k];
+            }
         }
     }
 }
@@ -268,8 +296,9 @@ cudaError_t sas_bin_init() {
 }
 
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
-                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, cudaStream_t st) {
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static, cudaStream_t st) {
     dim3 grid(T, I);
-    merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src, cap_all);
+    merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src, cap_all,
+                                                 fill_static);
     return cudaGetLastError();
 }

@@ -116,6 +116,23 @@ struct SasWork {
     unsigned comp_total, comp_take;
 };
 
+// Sub-tile granularity of the static shortcut: a 16x16 tile is 4 columns (4 px) x 8 rows (2 px) of
+// 4x2-pixel GROUPS.  The compositor gives each warp an 8x4 footprint (warp = (ry>>1)*2 + (cx>>1)) and
+// each of its four 8-lane groups one 4x2 block (group = (ry&1)*2 + (cx&1)); bit warp*4+group of a
+// tile's 32-bit mask says "some link Gaussian of this image can reach that block" (its culling
+// extents intersect it).  Blocks no link Gaussian can reach are pixel-identical to the view's
+// background-only tile and are copied instead of composited.
+__host__ __device__ __forceinline__ int sas_group_bit(int cx /*0..3*/, int ry /*0..7*/) {
+    return ((ry >> 1) * 2 + (cx >> 1)) * 4 + (ry & 1) * 2 + (cx & 1);
+}
+
+// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default = all on):
+//   bit 0  compositor: per-group (4x2) hit masks instead of one per warp footprint
+//   bit 1  group-level static shortcut (off: every group of a tile with link Gaussians is composited)
+//   bit 2  bucket-sort size classes run on concurrent streams (fork / join on the caller's stream)
+//   bit 3  merge skips tiles whose link bucket is empty (their ids are produced on demand for debug fetches)
+int sas_variant_flags();
+
 // Outputs of the compositor: per-image buffers (any may be null) ...
 struct SasOutputs {
     float *rgb, *depth, *alpha;
@@ -130,29 +147,34 @@ struct SasViewBuf {
 };
 
 // Launchers (each returns the cudaError_t of the launch).
-cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, int C, int I, int T, SasWork *work,
-                                  unsigned char *view_tile_needed, int *sort_list, int *comp_list, cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C, int I,
+                                  int W, int H, int tile_w, int tile_h, SasWork *work, unsigned char *view_tile_needed, int *sort_list,
+                                  int *comp_list, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *radii_out, unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st);
+                               unsigned int *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
+                               cudaStream_t st);
 cudaError_t sas_bin_init();
 cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,
                             unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,
                             unsigned int *row_tile_cursor, uint2 *pairs, long long capacity, cudaStream_t st);
 cudaError_t sas_sort_init(int n_sms);
+// aux / ev: SAS_SORT_CLASSES - 1 side streams and 2 * SAS_SORT_CLASSES events for the fork / join (may be null: serial)
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
-                                 long long capacity, cudaStream_t st, int *n_launches);
+                                 long long capacity, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
+// fill_static: also write the ids of tiles whose link bucket is empty (the compositor never reads those)
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
-                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, cudaStream_t st);
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static, cudaStream_t st);
 cudaError_t sas_composite_init(int n_sms);
 // Composites the ordered work list (image tiles with link Gaussians + the needed view tiles), then
 // copies the view tiles into the images whose link bucket for that tile is empty.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w,
-                                 int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out, SasViewBuf view_out,
-                                 long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st, int *n_launches);
+                                 const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
+                                 int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
+                                 SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
+                                 int *n_launches);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

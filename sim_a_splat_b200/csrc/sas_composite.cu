@@ -42,50 +42,90 @@ __device__ __forceinline__ unsigned char to_u8(float v) {
 
 struct Pixel {
     float pxf, pyf;            // pixel centre
-    float bx0, bx1, by0, by1;  // footprint bounds (first / last pixel centre of the warp's 8x4 block)
     float T, ar, ag, ab, ad;   // transmittance and accumulators
     int nc;
     bool done;
 };
 
-// Composite the cnt records of one staged batch into this lane's pixel (whole warp calls this).
-__device__ __forceinline__ void process_batch(const SasRecord *sb, int cnt, Pixel &p) {
-    const int lane = threadIdx.x & 31;
-    for (int j0 = 0; j0 < cnt; j0 += 32) {
-        bool hit = false;
-        if (j0 + lane < cnt) {
-            const float4 A = sb[j0 + lane].a;
-            const float4 B = sb[j0 + lane].b;
-            hit = (A.x + B.z >= p.bx0) && (A.x - B.z <= p.bx1) && (A.y + B.w >= p.by0) && (A.y - B.w <= p.by1);
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-            const int j = j0 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 A = sb[j].a;
-            const float4 B = sb[j].b;
-            const float dx = A.x - p.pxf, dy = A.y - p.pyf;
-            const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
-            if (!p.done && sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {
-                const float al = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg(-sigma));
-                if (al >= SAS_ALPHA_MIN) {
-                    const float nT = p.T * (1.0f - al);
-                    if (nT <= SAS_T_MIN) {
-                        p.done = true;
-                    } else {
-                        const float4 Cc = sb[j].c;
-                        const float vis = al * p.T;
-                        p.ar = fmaf(Cc.x, vis, p.ar);
-                        p.ag = fmaf(Cc.y, vis, p.ag);
-                        p.ab = fmaf(Cc.z, vis, p.ab);
-                        p.ad = fmaf(Cc.w, vis, p.ad);
-                        p.T = nT;
-                        p.nc++;
-                    }
-                }
+// Blend staged record j into this lane's pixel (gsplat rasterize_to_pixels inner body).
+__device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) {
+    const float4 A = sb[j].a;
+    const float4 B = sb[j].b;
+    const float dx = A.x - p.pxf, dy = A.y - p.pyf;
+    const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
+    if (!p.done && sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {
+        const float al = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg(-sigma));
+        if (al >= SAS_ALPHA_MIN) {
+            const float nT = p.T * (1.0f - al);
+            if (nT <= SAS_T_MIN) {
+                p.done = true;
+            } else {
+                const float4 Cc = sb[j].c;
+                const float vis = al * p.T;
+                p.ar = fmaf(Cc.x, vis, p.ar);
+                p.ag = fmaf(Cc.y, vis, p.ag);
+                p.ab = fmaf(Cc.z, vis, p.ab);
+                p.ad = fmaf(Cc.w, vis, p.ad);
+                p.T = nT;
+                p.nc++;
             }
         }
-        if (__all_sync(0xffffffffu, p.done)) break;
+    }
+}
+
+// Composite the cnt records of one staged batch into this lane's pixel (whole warp calls this).
+// X0, Y0: centre of the first pixel of the warp's 8x4 footprint.
+//
+// GROUPS = false: one hit mask per warp (the 8x4 footprint); every lane walks every hit.
+// GROUPS = true:  the footprint is split into four 4x2 blocks, one per 8-lane group (= one LDS.128
+//   phase, so the four groups reading four different records costs no extra shared-memory
+//   wavefronts); each group gets its own hit mask from four ballots and walks only its own hits, the
+//   groups diverge inside the 32-record chunk and reconverge after it.  CPU work model
+//   (tools/analyze_composite.py): 66 % of the per-warp walk iterations on the pusht batch.
+template <bool GROUPS>
+__device__ __forceinline__ void process_batch(const SasRecord *sb, int cnt, Pixel &p, float X0, float Y0) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const unsigned dm = __ballot_sync(0xffffffffu, p.done);
+        if (dm == 0xffffffffu) break;
+        if (GROUPS) {
+            bool hx0 = false, hx1 = false, hy0 = false, hy1 = false;
+            if (j0 + lane < cnt) {
+                const float4 A = sb[j0 + lane].a;
+                const float4 B = sb[j0 + lane].b;
+                const float xl = A.x - B.z, xh = A.x + B.z, yl = A.y - B.w, yh = A.y + B.w;
+                hx0 = (xh >= X0) && (xl <= X0 + 3.0f);
+                hx1 = (xh >= X0 + 4.0f) && (xl <= X0 + 7.0f);
+                hy0 = (yh >= Y0) && (yl <= Y0 + 1.0f);
+                hy1 = (yh >= Y0 + 2.0f) && (yl <= Y0 + 3.0f);
+            }
+            const unsigned b00 = __ballot_sync(0xffffffffu, hx0 && hy0);
+            const unsigned b10 = __ballot_sync(0xffffffffu, hx1 && hy0);
+            const unsigned b01 = __ballot_sync(0xffffffffu, hx0 && hy1);
+            const unsigned b11 = __ballot_sync(0xffffffffu, hx1 && hy1);
+            unsigned mask = (grp & 2) ? ((grp & 1) ? b11 : b01) : ((grp & 1) ? b10 : b00);
+            if (((dm >> (grp * 8)) & 0xffu) == 0xffu) mask = 0u;  // every pixel of this group has finished
+            while (mask) {  // groups diverge here; no warp-synchronous operation inside
+                const int j = j0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                blend_one(sb, j, p);
+            }
+            __syncwarp();
+        } else {
+            bool hit = false;
+            if (j0 + lane < cnt) {
+                const float4 A = sb[j0 + lane].a;
+                const float4 B = sb[j0 + lane].b;
+                hit = (A.x + B.z >= X0) && (A.x - B.z <= X0 + 7.0f) && (A.y + B.w >= Y0) && (A.y - B.w <= Y0 + 3.0f);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int j = j0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                blend_one(sb, j, p);
+            }
+        }
     }
 }
 
@@ -103,13 +143,13 @@ __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *sr
     sas_cp_async16(&dst->c, &src->c);
 }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool GROUPS>
 __global__ void __launch_bounds__(CB, MIN_CTAS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
-                 const int *__restrict__ comp_list, SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h,
-                 float bg0, float bg1, float bg2, SasOutputs img_out, SasViewBuf view_out, long long cap_src, long long cap_all,
-                 SasCounters *counters) {
+                 const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_list, SasWork *work, int n_bg, int n_dyn,
+                 int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
+                 SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters) {
     __shared__ SasRecord stage[2][CB];
     __shared__ unsigned s_take;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,6 +170,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         int out_img, tile, v;
         const int *gids;   // gid of entry e is gids[e * gstride]
         int gstride, n;
+        unsigned dyn_mask = 0xffffffffu;  // bit (warp*4 + group): a link Gaussian of this image can touch the group's 4x2 block
         if (is_view) {
             const long long vt = item - IT;
             v = (int)(vt / T); tile = (int)(vt - (long long)v * T);
@@ -151,6 +192,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             gids = merged_gid + off;
             gstride = 1;
             n = (int)(end - off);
+            dyn_mask = tile_dyn_mask[item];
         }
         // background records live per view, link records per image; a merged id below n_bg selects the former
         const SasRecord *rec_bg = rec + (size_t)v * n_bg;
@@ -158,17 +200,21 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
 #define SAS_REC_OF(gid) (((gid) < n_bg ? rec_bg : rec_dy) + (gid))
 
         // ---- this lane's pixel ----
+        // warp = 8x4 footprint; its four 8-lane groups own the four 4x2 blocks of it (sas_common.cuh: sas_group_bit)
         const int ty = tile / tile_w, tx = tile - ty * tile_w;
         const int fx = tx * SAS_TILE_PX + (warp & 1) * 8, fy = ty * SAS_TILE_PX + (warp >> 1) * 4;  // 8 wide x 4 high
-        const int px = fx + (lane & 7), py = fy + (lane >> 3);
+        const int grp = lane >> 3, gl = lane & 7;
+        const int px = fx + (grp & 1) * 4 + (gl & 3), py = fy + (grp >> 1) * 2 + (gl >> 2);
         const bool inside = (px < W) && (py < H);
+        // A group no link Gaussian of this image can touch is pixel-identical to the view's
+        // background-only tile: it is skipped here and copied afterwards (copy_static_tiles_kernel).
+        const bool group_static = ((dyn_mask >> (warp * 4 + grp)) & 1u) == 0u;
+        const float X0 = (float)fx + 0.5f, Y0 = (float)fy + 0.5f;
         Pixel p;
         p.pxf = (float)px + 0.5f; p.pyf = (float)py + 0.5f;
-        p.bx0 = (float)fx + 0.5f; p.bx1 = (float)fx + 7.5f;
-        p.by0 = (float)fy + 0.5f; p.by1 = (float)fy + 3.5f;
         p.T = 1.0f; p.ar = p.ag = p.ab = p.ad = 0.0f;
         p.nc = 0;
-        p.done = !inside;
+        p.done = !inside || group_static;
 
         // ---- batches: prologue puts batch 0 in flight and the id of batch 1 in a register ----
         const int nb = (n + CB - 1) / CB;
@@ -190,12 +236,12 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
             if (__all_sync(0xffffffffu, p.done)) continue;  // whole warp finished: only keep feeding the pipeline
-            process_batch(stage[buf], cnt, p);
+            process_batch<GROUPS>(stage[buf], cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
 #undef SAS_REC_OF
 
-        if (inside) {
+        if (inside && !group_static) {
             const size_t pi = ((size_t)out_img * H + py) * W + px;
             const float Aout = 1.0f - p.T;
             const float depth = p.ad / fmaxf(Aout, 1e-10f);
@@ -215,15 +261,20 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
 // Images whose link bucket for a tile is empty take the tile from their view's buffers; the
 // background blend and alpha = 1 - T are computed from the stored T exactly as the compositor does.
 __global__ void __launch_bounds__(CB) copy_static_tiles_kernel(const unsigned int *__restrict__ row_tile_count, const int *__restrict__ view_of_image,
-                                                               int C, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2,
-                                                               SasOutputs img_out, SasViewBuf view_out) {
+                                                               const unsigned int *__restrict__ tile_dyn_mask, int C, int W, int H, int tile_w,
+                                                               int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
+                                                               SasViewBuf view_out) {
     const int tile = blockIdx.x, im = blockIdx.y;
     const int T = tile_w * tile_h;
-    if (row_tile_count[(size_t)(C + im) * T + tile] != 0u) return;  // composited from its own merged list
+    // tiles with link Gaussians were composited from their merged list, except the 4x2 groups none of them can touch
+    const unsigned dyn = row_tile_count[(size_t)(C + im) * T + tile] != 0u ? tile_dyn_mask[(size_t)im * T + tile] : 0u;
+    if (dyn == 0xffffffffu) return;
     const int v = view_of_image[im];
     const int ty = tile / tile_w, tx = tile - ty * tile_w;
-    const int px = tx * SAS_TILE_PX + (threadIdx.x & 15), py = ty * SAS_TILE_PX + (threadIdx.x >> 4);
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int px = tx * SAS_TILE_PX + lx, py = ty * SAS_TILE_PX + ly;
     if (px >= W || py >= H) return;
+    if ((dyn >> sas_group_bit(lx >> 2, ly >> 1)) & 1u) return;
     const size_t pi = ((size_t)im * H + py) * W + px, pv = ((size_t)v * H + py) * W + px;
     if (row_tile_count[(size_t)v * T + tile] == 0u) {  // nothing at all in this tile: T = 1, accumulators 0
         write_pixel(img_out, pi, fmaf(1.0f, bg0, 0.0f), fmaf(1.0f, bg1, 0.0f), fmaf(1.0f, bg2, 0.0f), 0.0f, 0.0f, 0);
@@ -264,16 +315,6 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 
 int g_comp_sms = 148;
 
-int composite_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SAS_COMPOSITE");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 1) v = 1;
-    }
-    return v;
-}
-
 }  // namespace
 
 cudaError_t sas_composite_init(int n_sms) {
@@ -281,20 +322,22 @@ cudaError_t sas_composite_init(int n_sms) {
     return cudaSuccess;
 }
 
-// Register budget variant: environment variable SAS_COMPOSITE (read once): 1 = registers capped for
-// 8 resident CTAs/SM (default, measured 4.5 % faster), 0 = 6 CTAs/SM.
+// Registers are capped for 8 resident CTAs/SM (measured 4.5 % faster than 6).  SAS_VARIANT bit 0
+// (sas_common.cuh) selects the per-group hit masks.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w,
-                                 int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out, SasViewBuf view_out,
-                                 long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st, int *n_launches) {
-#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, comp_list, work, n_bg, n_dyn, C, I, W, H, tile_w, \
-                 tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
-    if (composite_variant() == 0) composite_kernel<6><<<g_comp_sms * 6, CB, 0, st>>>(SAS_ARGS);
-    else composite_kernel<8><<<g_comp_sms * 8, CB, 0, st>>>(SAS_ARGS);
+                                 const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
+                                 int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
+                                 SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
+                                 int *n_launches) {
+#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
+                 tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
+    if (sas_variant_flags() & 1) composite_kernel<8, true><<<g_comp_sms * 8, CB, 0, st>>>(SAS_ARGS);
+    else composite_kernel<8, false><<<g_comp_sms * 8, CB, 0, st>>>(SAS_ARGS);
 #undef SAS_ARGS
     dim3 grid(tile_w * tile_h, I);
-    copy_static_tiles_kernel<<<grid, CB, 0, st>>>(row_tile_count, view_of_image, C, W, H, tile_w, tile_h, bg0, bg1, bg2, img_out, view_out);
+    copy_static_tiles_kernel<<<grid, CB, 0, st>>>(row_tile_count, view_of_image, tile_dyn_mask, C, W, H, tile_w, tile_h, bg0, bg1, bg2, img_out,
+                                                  view_out);
     if (n_launches) *n_launches += 2;
     return cudaGetLastError();
 }

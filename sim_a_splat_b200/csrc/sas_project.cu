@@ -50,7 +50,7 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
                                             const float4 *__restrict__ scale_link, const float *__restrict__ sh_planes, int n_pad, int g,
                                             size_t ig, const float *__restrict__ link_poses, int L, const SasCamera *__restrict__ cam, int W,
                                             int H, int tile_w, int tile_h, SasRecord *__restrict__ rec, uint2 *__restrict__ bins,
-                                            unsigned int *__restrict__ radii_out, int &x0, int &y0, int &x1, int &y1) {
+                                            unsigned int *__restrict__ radii_out, int &x0, int &y0, int &x1, int &y1, float4 &reach) {
 
     const float4 mo = __ldg(mean_op + g);
     const float4 qq = __ldg(quat + g);
@@ -209,7 +209,30 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
     r.b = make_float4(0.5f * (a / det), mo.w, ex, ey);
     r.c = make_float4(col[0], col[1], col[2], czm);
     rec[ig] = r;
+    reach = make_float4(m2x - ex, m2x + ex, m2y - ey, m2y + ey);
     return true;
+}
+
+// Which 4x2-pixel groups of the tile at pixel origin (tx0, ty0) the Gaussian's culling extents reach
+// (bit layout: sas_common.cuh sas_group_bit).  Same comparisons as the compositor's per-group test.
+__device__ __forceinline__ unsigned group_reach_mask(const float4 reach, int tx0, int ty0) {
+    unsigned xm = 0u, ym = 0u;
+#pragma unroll
+    for (int cx = 0; cx < 4; cx++) {
+        const float c0 = (float)(tx0 + 4 * cx) + 0.5f;
+        if (reach.y >= c0 && reach.x <= c0 + 3.0f) xm |= 1u << cx;
+    }
+#pragma unroll
+    for (int ry = 0; ry < 8; ry++) {
+        const float r0 = (float)(ty0 + 2 * ry) + 0.5f;
+        if (reach.w >= r0 && reach.z <= r0 + 1.0f) ym |= 1u << ry;
+    }
+    const unsigned xs = (xm & 3u) | (((xm >> 2) & 3u) << 4);  // columns 0,1 -> bits 0,1; columns 2,3 -> bits 4,5
+    unsigned m = 0u;
+#pragma unroll
+    for (int ry = 0; ry < 8; ry++)
+        if ((ym >> ry) & 1u) m |= xs << ((ry >> 1) * 8 + (ry & 1) * 2);
+    return m;
 }
 
 constexpr int PROJ_FAST_TILES = 4;  // Gaussians covering at most this many tiles count through shared memory
@@ -225,25 +248,43 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
                const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
                const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
                uint2 *__restrict__ bins, unsigned int *__restrict__ radii_out, unsigned int *__restrict__ row_tile_count,
-               SasCounters *counters, int smem_tiles) {
-    extern __shared__ unsigned int s_cnt[];  // [smem_tiles] (0 = direct global counting)
+               unsigned int *__restrict__ tile_dyn_mask, SasCounters *counters, int smem_tiles, int smem_masks) {
+    extern __shared__ unsigned int s_cnt[];  // [smem_tiles] counts (0 = direct global counting), then [smem_tiles] group masks if smem_masks
+    unsigned int *s_mask = s_cnt + smem_tiles;
     const int T = tile_w * tile_h;
-    for (int t = threadIdx.x; t < smem_tiles; t += 256) s_cnt[t] = 0u;
+    for (int t = threadIdx.x; t < smem_tiles * (1 + smem_masks); t += 256) s_cnt[t] = 0u;
     if (smem_tiles) __syncthreads();
 
     const int local = blockIdx.x * 256 + threadIdx.x;
     const int row = blockIdx.y;
     bool vis = false;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    float4 reach = make_float4(0.f, 0.f, 0.f, 0.f);
     if (local < span.n)
         vis = project_one<DEG>(mean_op, quat, scale_link, sh_planes, n_pad, span.g0 + local,
                                (size_t)span.rec0 + (size_t)row * span.n + local, link_poses, L, row_cams + span.row0 + row, W, H, tile_w,
-                               tile_h, rec, bins, radii_out, x0, y0, x1, y1);
+                               tile_h, rec, bins, radii_out, x0, y0, x1, y1, reach);
     unsigned int *tc = row_tile_count + (size_t)(span.row0 + row) * T;
+    // link span only (rows = images): per-(image,tile) mask of the 4x2 groups a link Gaussian can reach
+    unsigned int *dm = tile_dyn_mask ? tile_dyn_mask + (size_t)row * T : nullptr;
     if (vis) {
-        const bool fast = smem_tiles && (x1 - x0) * (y1 - y0) <= PROJ_FAST_TILES;
+        const int ntile = (x1 - x0) * (y1 - y0);
+        const bool fast = smem_tiles && ntile <= PROJ_FAST_TILES;
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) atomicAdd((fast ? s_cnt : tc) + y * tile_w + x, 1u);
+            for (int x = x0; x < x1; x++) {
+                const int t = y * tile_w + x;
+                atomicAdd((fast ? s_cnt : tc) + t, 1u);
+                if (dm) {
+                    // screen-filling Gaussians: call every group reachable instead of testing hundreds of tiles
+                    const unsigned m = ntile <= 64 ? group_reach_mask(reach, x * SAS_TILE_PX, y * SAS_TILE_PX) : 0xffffffffu;
+                    // read first: after the first few Gaussians of a CTA the bits are already set
+                    if (smem_masks) {
+                        if ((s_mask[t] & m) != m) atomicOr(s_mask + t, m);
+                    } else if ((__ldcg(dm + t) & m) != m) {
+                        atomicOr(dm + t, m);
+                    }
+                }
+            }
     }
     {  // one counter update per warp instead of one per thread
         const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -254,6 +295,10 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
         for (int t = threadIdx.x; t < smem_tiles; t += 256) {
             const unsigned c = s_cnt[t];
             if (c) atomicAdd(tc + t, c);
+            if (dm && smem_masks) {
+                const unsigned m = s_mask[t];
+                if (m) atomicOr(dm + t, m);
+            }
         }
     }
 }
@@ -263,12 +308,14 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *radii_out, unsigned int *row_tile_count, SasCounters *counters, cudaStream_t st) {
+                               unsigned int *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
+                               cudaStream_t st) {
     if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
     dim3 grid((span.n + 255) / 256, span.rows);
     const int T = tile_w * tile_h;
     const int smem_tiles = T <= SAS_SMEM_TILES_MAX ? T : 0;
-    const size_t smem = (size_t)smem_tiles * sizeof(unsigned int);
+    const int smem_masks = (tile_dyn_mask && smem_tiles && T <= SAS_SMEM_TILES_MAX / 2) ? 1 : 0;  // stays under the 48 KB default limit
+    const size_t smem = (size_t)smem_tiles * (1 + smem_masks) * sizeof(unsigned int);
     // SAS_PROJECT=n (environment, read once): minimum resident CTAs/SM the register allocation targets (3, 4 or 5).
     static int variant = -1;
     if (variant < 0) {
@@ -276,7 +323,8 @@ cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const 
         variant = e ? atoi(e) : 4;
         if (variant < 3 || variant > 5) variant = 4;
     }
-#define SAS_PROJ_ARGS mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, H, tile_w, tile_h, rec, bins, radii_out,                       row_tile_count, counters, smem_tiles
+#define SAS_PROJ_ARGS mean_op, quat, scale_link, sh_planes, n_pad, span, link_poses, L, row_cams, W, H, tile_w, tile_h, rec, bins, radii_out, \
+                      row_tile_count, tile_dyn_mask, counters, smem_tiles, smem_masks
 #define SAS_PROJ(D)                                                                              \
     do {                                                                                         \
         if (variant == 3) project_kernel<D, 3><<<grid, 256, smem, st>>>(SAS_PROJ_ARGS);          \

@@ -195,19 +195,41 @@ cudaError_t sas_sort_init(int n_sms) {
     return e;
 }
 
+// The five size classes touch disjoint buckets, so with side streams they run concurrently
+// (fork on an event of the caller's stream, join back into it): the step pays for the slowest class
+// instead of the sum of five partially filled launches.
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
-                                 long long capacity, cudaStream_t st, int *n_launches) {
+                                 long long capacity, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches) {
     // grid = SMs x resident CTAs of the class (threads / shared memory bound)
     const int sms = g_sort_sms;
-    tile_sort_kernel<128, false><<<sms * 16, 128, sort_smem<128>(SAS_SORT_CAP0), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 0,
-                                                                                     SAS_SORT_CAP0, capacity);
-    tile_sort_kernel<256, false><<<sms * 5, 256, sort_smem<256>(SAS_SORT_CAP1), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 1,
-                                                                                    SAS_SORT_CAP1, capacity);
-    tile_sort_kernel<512, false><<<sms * 2, 512, sort_smem<512>(SAS_SORT_CAP2), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 2,
-                                                                                    SAS_SORT_CAP2, capacity);
-    tile_sort_kernel<512, false><<<sms, 512, sort_smem<512>(SAS_SORT_CAP3), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 3,
-                                                                                SAS_SORT_CAP3, capacity);
-    tile_sort_kernel<512, true><<<sms, 512, sizeof(SortShared<512>), st>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0, capacity);
+    const bool fork = aux != nullptr && ev != nullptr && (sas_variant_flags() & 4);
+    cudaError_t e;
+    if (fork && (e = cudaEventRecord(ev[0], st)) != cudaSuccess) return e;
+    // class -> stream: the class with the longest critical path (<= 5632 entries, two CTAs per SM) stays on the caller's stream
+    cudaStream_t s_of[SAS_SORT_CLASSES] = {st, st, st, st, st};
+    if (fork) {
+        const int side[4] = {0, 1, 3, 4};
+        for (int k = 0; k < 4; k++) {
+            s_of[side[k]] = aux[k];
+            if ((e = cudaStreamWaitEvent(aux[k], ev[0], 0)) != cudaSuccess) return e;
+        }
+    }
+    tile_sort_kernel<512, false><<<sms * 2, 512, sort_smem<512>(SAS_SORT_CAP2), s_of[2]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 2,
+                                                                                         SAS_SORT_CAP2, capacity);
+    tile_sort_kernel<512, false><<<sms, 512, sort_smem<512>(SAS_SORT_CAP3), s_of[3]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 3,
+                                                                                     SAS_SORT_CAP3, capacity);
+    tile_sort_kernel<256, false><<<sms * 5, 256, sort_smem<256>(SAS_SORT_CAP1), s_of[1]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 1,
+                                                                                         SAS_SORT_CAP1, capacity);
+    tile_sort_kernel<128, false><<<sms * 16, 128, sort_smem<128>(SAS_SORT_CAP0), s_of[0]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 0,
+                                                                                          SAS_SORT_CAP0, capacity);
+    tile_sort_kernel<512, true><<<sms, 512, sizeof(SortShared<512>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0,
+                                                                               capacity);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (fork)
+        for (int k = 0; k < 4; k++) {
+            if ((e = cudaEventRecord(ev[1 + k], aux[k])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(st, ev[1 + k], 0)) != cudaSuccess) return e;
+        }
     if (n_launches) *n_launches += 5;
     return cudaGetLastError();
 }

@@ -8,8 +8,10 @@
 //     the ideal makespan on the pusht batch).  Two kinds of item:
 //       * image tile (i,t) whose link bucket is non-empty: composited from its merged list;
 //       * view tile (v,t): background-only compositing, done ONCE per view for all the images of
-//         that view whose link bucket for tile t is empty (47 % of the pusht batch) -- their pixels
-//         are bit-identical, so they are copied (sas_composite.cu: copy_static_tiles_kernel).
+//         that view whose link bucket for tile t is empty (47 % of the pusht batch), and for the
+//         4x2-pixel groups of the other tiles that no link Gaussian can reach (tile_dyn_mask, written
+//         by the projection kernel) -- their pixels are bit-identical, so they are copied
+//         (sas_composite.cu: copy_static_tiles_kernel).
 //
 // All counts come from the row-tile counts written by the projection kernel; nothing here reads
 // back to the host.
@@ -34,9 +36,21 @@ __device__ __forceinline__ int comp_class_of(unsigned n) {
     return 31 - w;
 }
 
+// groups of tile t that have at least one pixel inside the image (ragged right / bottom edge)
+__device__ __forceinline__ unsigned inside_group_mask(int t, int tile_w, int W, int H) {
+    const int ty = t / tile_w, tx = t - ty * tile_w;
+    if ((tx + 1) * SAS_TILE_PX <= W && (ty + 1) * SAS_TILE_PX <= H) return 0xffffffffu;
+    unsigned m = 0u;
+    for (int ry = 0; ry < 8; ry++)
+        for (int cx = 0; cx < 4; cx++)
+            if (tx * SAS_TILE_PX + 4 * cx < W && ty * SAS_TILE_PX + 2 * ry < H) m |= 1u << sas_group_bit(cx, ry);
+    return m;
+}
+
 // pass 1 over [0, RT) row buckets then [RT, RT+IT) image tiles: class histograms + the 'needed' marks
 __global__ void __launch_bounds__(256) work_count_kernel(const unsigned *__restrict__ row_tile_count, const int *__restrict__ view_of_image,
-                                                         int C, int I, int T, SasWork *work, unsigned char *__restrict__ view_tile_needed) {
+                                                         const unsigned *__restrict__ tile_dyn_mask, int C, int I, int T, int tile_w, int W,
+                                                         int H, SasWork *work, unsigned char *__restrict__ view_tile_needed) {
     __shared__ unsigned s_sort[SAS_SORT_CLASSES], s_comp[SAS_COMP_CLASSES];
     if (threadIdx.x < SAS_SORT_CLASSES) s_sort[threadIdx.x] = 0;
     if (threadIdx.x < SAS_COMP_CLASSES) s_comp[threadIdx.x] = 0;
@@ -53,6 +67,8 @@ __global__ void __launch_bounds__(256) work_count_kernel(const unsigned *__restr
         const unsigned nd = row_tile_count[(size_t)(C + i) * T + t];
         if (nd > 0) {
             atomicAdd(&s_comp[comp_class_of(nd + row_tile_count[(size_t)v * T + t])], 1u);
+            // some visible group is out of reach of every link Gaussian: it is copied from the view tile
+            if (~tile_dyn_mask[j] & inside_group_mask(t, tile_w, W, H)) view_tile_needed[(size_t)v * T + t] = 1;
         } else {
             view_tile_needed[(size_t)v * T + t] = 1;  // benign race: every writer stores 1
         }
@@ -118,12 +134,15 @@ __global__ void __launch_bounds__(256) work_scatter_kernel(const unsigned *__res
 
 }  // namespace
 
-cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, int C, int I, int T, SasWork *work,
-                                  unsigned char *view_tile_needed, int *sort_list, int *comp_list, cudaStream_t st, int *n_launches) {
+cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C, int I,
+                                  int W, int H, int tile_w, int tile_h, SasWork *work, unsigned char *view_tile_needed, int *sort_list,
+                                  int *comp_list, cudaStream_t st, int *n_launches) {
+    const int T = tile_w * tile_h;
     const long long RT = (long long)(C + I) * T, IT = (long long)I * T, VT = (long long)C * T;
     cudaError_t e = cudaMemsetAsync(view_tile_needed, 0, (size_t)VT, st);
     if (e != cudaSuccess) return e;
-    work_count_kernel<<<(unsigned)((RT + IT + 255) / 256), 256, 0, st>>>(row_tile_count, view_of_image, C, I, T, work, view_tile_needed);
+    work_count_kernel<<<(unsigned)((RT + IT + 255) / 256), 256, 0, st>>>(row_tile_count, view_of_image, tile_dyn_mask, C, I, T, tile_w, W, H, work,
+                                                                            view_tile_needed);
     work_count_views_kernel<<<(unsigned)((VT + 255) / 256), 256, 0, st>>>(row_tile_count, C, T, work, view_tile_needed);
     work_prefix_kernel<<<1, 32, 0, st>>>(work);
     work_scatter_kernel<<<(unsigned)((RT + IT + VT + 255) / 256), 256, 0, st>>>(row_tile_count, view_of_image, C, I, T, work, view_tile_needed,
