@@ -120,6 +120,33 @@ void sas_destroy(sas_renderer *r);
  * mu' = rot*mu + pos, Sigma' = rot*Sigma*rot^T for every Gaussian of link l. */
 int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem, void *stream);
 
+/* Replaces: the pose algebra of SplatHandler.draw_handler itself (splat_handler.py:250-281), run on the
+ * device for all envs at once.  The model holds the constants of _load_saved_masks (:62-83: scale_factor,
+ * Ri, ti), the weld translation (:229-235; its rotation must be identity, as the reference asserts) and the
+ * capture-time visual-mesh FK of _add_robot_meshes (:158-163, :197).  HOST pointers; copied. */
+typedef struct {
+    int32_t n_links;          /* must equal the scene's L; link l is driven by the l-th robot body of the draw message */
+    double scale;             /* s  */
+    double Ri[9];             /* row-major */
+    double ti[3];
+    double weld_t[3];
+    const double *fk_R;       /* [L,9] row-major */
+    const double *fk_t;       /* [L,3] */
+} sas_pose_model;
+int sas_set_pose_model(sas_renderer *r, const sas_pose_model *model);
+
+/* body poses [n_envs, L, 7] fp64 = (quaternion wxyz as sent -- normalised here, :239-240 -- | position xyz), the
+ * fields of lcmt_viewer_draw for the robot's bodies (manipulator_env.py:377-390).  Computes
+ * rot = Ri Rm Rfk^T Ri^T, pos = -rot ti - s Ri Rm Rfk^T tfk + s Ri (p + weld_t) + ti in fp64 and stores the
+ * fp32 [n_envs, L, 12] block sas_set_link_poses would have been given. */
+int sas_set_link_poses_from_bodies(sas_renderer *r, const double *body_wxyz_xyz, int n_envs, int mem, void *stream);
+
+/* Replaces: the pinhole unprojection of GaussianSplat.generate_RGBD_point_cloud (nerfstudio_utils.py:441-452):
+ * xyz[i,v,u] = ((u-cx) d/fx, (v-cy) d/fy, d) in the camera frame (OpenCV axes), valid = d < max_depth.
+ * K row-major [9]; depth [I,H,W], xyz [I,H,W,3], valid [I,H,W] (may be NULL); all in `mem`. */
+int sas_unproject_depth(sas_renderer *r, const float *depth, int n_images, int width, int height, const float *K, float max_depth,
+                        float *xyz, uint8_t *valid, int mem, void *stream);
+
 /* Replaces: the (height,width,wxyz,position) arguments of client.get_render
  * (splat_env_wrapper.py:148-157) / the Cameras(...) built in GaussianSplat.render
  * (nerfstudio_utils.py:125-138), batched.  HOST pointers.  viewmats [I,16] are
@@ -149,6 +176,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out);
 #define SAS_DBG_SORTED_GIDS 4  /* [M] i32 canonical Gaussian index per intersection, (image,tile,depth,gid) order */
 #define SAS_DBG_VIEW_OF_IMAGE 5 /* [I] i32 */
 #define SAS_DBG_RADII 6     /* same rows as the records, u32: radius_x | radius_y << 16 (gsplat radii; undefined where culled) */
+#define SAS_DBG_LINK_POSES 7 /* [n_envs, L, 12] f32: the link poses in effect (as set, or as composed from body poses) */
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
 
 /* Per-stage device timing (CUDA events on the caller's stream around each stage of sas_render).

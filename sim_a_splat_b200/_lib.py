@@ -20,9 +20,11 @@ SAS_DBG_TILE_OFFSETS = 3
 SAS_DBG_SORTED_GIDS = 4
 SAS_DBG_VIEW_OF_IMAGE = 5
 SAS_DBG_RADII = 6
+SAS_DBG_LINK_POSES = 7
 
 EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
+    "sas_set_pose_model", "sas_set_link_poses_from_bodies", "sas_unproject_depth",
     "sas_get_stats", "sas_set_stage_timing", "sas_get_stage_ms", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
 ]
 
@@ -49,6 +51,11 @@ class Stats(C.Structure):
                 ("n_staged", C.c_int64), ("overflow", C.c_int32), ("n_images", C.c_int32), ("n_views", C.c_int32),
                 ("n_gaussians", C.c_int32), ("n_background", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
+
+
+class PoseModel(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("scale", C.c_double), ("Ri", C.c_double * 9), ("ti", C.c_double * 3),
+                ("weld_t", C.c_double * 3), ("fk_R", C.c_void_p), ("fk_t", C.c_void_p)]
 
 
 class SasError(RuntimeError):
@@ -81,6 +88,12 @@ def load(build_if_missing: bool = True):
     lib.sas_destroy.restype = None
     lib.sas_set_link_poses.argtypes = [P, P, C.c_int, C.c_int, P]
     lib.sas_set_link_poses.restype = C.c_int
+    lib.sas_set_pose_model.argtypes = [P, C.POINTER(PoseModel)]
+    lib.sas_set_pose_model.restype = C.c_int
+    lib.sas_set_link_poses_from_bodies.argtypes = [P, P, C.c_int, C.c_int, P]
+    lib.sas_set_link_poses_from_bodies.restype = C.c_int
+    lib.sas_unproject_depth.argtypes = [P, P, C.c_int, C.c_int, C.c_int, P, C.c_float, P, P, C.c_int, P]
+    lib.sas_unproject_depth.restype = C.c_int
     lib.sas_set_cameras.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, P]
     lib.sas_set_cameras.restype = C.c_int
     lib.sas_render.argtypes = [P, C.POINTER(Outputs), P]

@@ -44,6 +44,9 @@ struct sas_renderer {
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
     DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask;
+    SasPoseModel pose_model{};            // device pointers inside; pose_model.L == 0: not set
+    double *fk_dev = nullptr;             // [L,12]: fk_R then fk_t
+    DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
     cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
@@ -128,7 +131,7 @@ int sas_variant_flags() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SAS_VARIANT");
-        v = e ? (int)strtol(e, nullptr, 0) & 0xff : 0xff;
+        v = e ? (int)strtol(e, nullptr, 0) & 0xff : 0xcf;
     }
     return v;
 }
@@ -238,6 +241,7 @@ void sas_destroy(sas_renderer *r) {
     cudaSetDevice(r->device);
     cudaDeviceSynchronize();
     cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
+    cudaFree(r->fk_dev);
     cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters);
     if (r->stage_host) cudaFreeHost(r->stage_host);
     if (r->cams_copied) cudaEventDestroy(r->cams_copied);
@@ -249,7 +253,7 @@ void sas_destroy(sas_renderer *r) {
         if (s) cudaStreamDestroy(s);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc,
-                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask};
+                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -270,6 +274,72 @@ int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem,
     SAS_CUDA(r, cudaMemcpyAsync(r->link_poses, poses, sizeof(float) * 12 * (size_t)n_envs * r->L,
                                 mem == SAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
     r->n_envs = n_envs;
+    return SAS_OK;
+}
+
+int sas_set_pose_model(sas_renderer *r, const sas_pose_model *model) {
+    if (!r || !model) return SAS_EINVAL;
+    if (model->n_links != r->L || r->L <= 0 || !model->fk_R || !model->fk_t)
+        return fail(r, SAS_EINVAL, "sas_set_pose_model: n_links must equal the scene's link count (> 0) and fk_R / fk_t must be given");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    if (!r->fk_dev) SAS_CUDA(r, cudaMalloc(&r->fk_dev, sizeof(double) * 12 * (size_t)r->L));
+    SAS_CUDA(r, cudaMemcpy(r->fk_dev, model->fk_R, sizeof(double) * 9 * (size_t)r->L, cudaMemcpyHostToDevice));
+    SAS_CUDA(r, cudaMemcpy(r->fk_dev + 9 * (size_t)r->L, model->fk_t, sizeof(double) * 3 * (size_t)r->L, cudaMemcpyHostToDevice));
+    SasPoseModel &m = r->pose_model;
+    m.L = r->L;
+    m.s = model->scale;
+    for (int i = 0; i < 9; i++) m.Ri[i] = model->Ri[i];
+    for (int i = 0; i < 3; i++) { m.ti[i] = model->ti[i]; m.weld_t[i] = model->weld_t[i]; }
+    m.fk_R = r->fk_dev;
+    m.fk_t = r->fk_dev + 9 * (size_t)r->L;
+    return SAS_OK;
+}
+
+int sas_set_link_poses_from_bodies(sas_renderer *r, const double *body, int n_envs, int mem, void *stream) {
+    if (!r) return SAS_EINVAL;
+    if (r->pose_model.L == 0) return fail(r, SAS_ESTATE, "sas_set_link_poses_from_bodies: sas_set_pose_model has not been called");
+    if (!body || n_envs <= 0) return fail(r, SAS_EINVAL, "sas_set_link_poses_from_bodies: null poses or n_envs <= 0");
+    const int maxE = r->cfg.max_envs > 0 ? r->cfg.max_envs : 1;
+    if (n_envs > maxE) return fail(r, SAS_ECAPACITY, "sas_set_link_poses_from_bodies: n_envs exceeds max_envs");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *d_body = body;
+    if (mem != SAS_MEM_DEVICE) {
+        const size_t bytes = sizeof(double) * 7 * (size_t)n_envs * r->L;
+        int rc;
+        if ((rc = ensure(r, r->body_dev, bytes))) return rc;
+        SAS_CUDA(r, cudaMemcpyAsync(r->body_dev.p, body, bytes, cudaMemcpyHostToDevice, st));
+        d_body = (const double *)r->body_dev.p;
+    }
+    SAS_CUDA(r, sas_launch_link_poses(d_body, r->pose_model, n_envs, r->link_poses, st));
+    r->n_envs = n_envs;
+    return SAS_OK;
+}
+
+int sas_unproject_depth(sas_renderer *r, const float *depth, int n_images, int width, int height, const float *K, float max_depth,
+                        float *xyz, uint8_t *valid, int mem, void *stream) {
+    if (!r) return SAS_EINVAL;
+    if (!depth || !xyz || !K || n_images <= 0 || width <= 0 || height <= 0) return fail(r, SAS_EINVAL, "sas_unproject_depth: bad argument");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = (size_t)n_images * width * height;
+    const float *d_depth = depth;
+    float *d_xyz = xyz;
+    uint8_t *d_valid = valid;
+    if (mem != SAS_MEM_DEVICE) {
+        int rc;
+        if ((rc = ensure(r, r->unproj_d, P * 4))) return rc;
+        if ((rc = ensure(r, r->unproj_xyz, P * 12))) return rc;
+        if (valid && (rc = ensure(r, r->unproj_valid, P))) return rc;
+        SAS_CUDA(r, cudaMemcpyAsync(r->unproj_d.p, depth, P * 4, cudaMemcpyHostToDevice, st));
+        d_depth = (const float *)r->unproj_d.p; d_xyz = (float *)r->unproj_xyz.p; d_valid = valid ? (uint8_t *)r->unproj_valid.p : nullptr;
+    }
+    SAS_CUDA(r, sas_launch_unproject(d_depth, n_images, width, height, K[0], K[4], K[2], K[5], max_depth, d_xyz, d_valid, st));
+    if (mem != SAS_MEM_DEVICE) {
+        SAS_CUDA(r, cudaMemcpyAsync(xyz, d_xyz, P * 12, cudaMemcpyDeviceToHost, st));
+        if (valid) SAS_CUDA(r, cudaMemcpyAsync(valid, d_valid, P, cudaMemcpyDeviceToHost, st));
+        SAS_CUDA(r, cudaStreamSynchronize(st));
+    }
     return SAS_OK;
 }
 
@@ -473,7 +543,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
     out->n_isects = (int64_t)c.n_isects;
     out->n_isects_src = (int64_t)c.n_isects_src;
     out->n_visible_src = (int64_t)c.n_visible_src;
-    out->n_staged = (int64_t)c.n_staged;
+    out->n_staged = (int64_t)(c.n_staged / 8);  // the compositor counts per strip of WARPS/8 of a tile
     out->max_tile_list = (int64_t)c.max_tile_list;
     out->overflow = (int32_t)c.overflow;
     out->n_images = r->I; out->n_views = r->C; out->n_gaussians = r->N; out->n_background = r->n_bg;
@@ -483,9 +553,15 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
 
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
     if (!r || !dst_host) return SAS_EINVAL;
-    if (!r->rendered) return fail(r, SAS_ESTATE, "sas_debug_fetch: nothing rendered yet");
     SAS_CUDA(r, cudaSetDevice(r->device));
     SAS_CUDA(r, cudaDeviceSynchronize());
+    if (what == SAS_DBG_LINK_POSES) {
+        const size_t avail = sizeof(float) * 12 * (size_t)r->n_envs * r->L;
+        if (bytes > avail) return fail(r, SAS_EINVAL, "sas_debug_fetch: more bytes requested than available");
+        if (bytes) SAS_CUDA(r, cudaMemcpy(dst_host, r->link_poses, bytes, cudaMemcpyDeviceToHost));
+        return SAS_OK;
+    }
+    if (!r->rendered) return fail(r, SAS_ESTATE, "sas_debug_fetch: nothing rendered yet");
     const size_t T = (size_t)r->tile_w * r->tile_h;
     const size_t n_rec = (size_t)r->C * r->n_bg + (size_t)r->I * r->n_dyn, IT = (size_t)r->I * T;
     const void *src = nullptr;

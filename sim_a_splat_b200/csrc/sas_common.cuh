@@ -58,7 +58,11 @@ struct __align__(16) SasRecord {
 __device__ __forceinline__ float sas_exp_neg(float x) {
     float t = x * 1.44269502162933349609375f;
     t = fmaxf(t, -125.0f);
-    float n = rintf(t);
+    // rintf(t) as (t + 1.5*2^23) - 1.5*2^23: the same round-to-nearest-even integer for |t| < 2^22, on the
+    // FMA pipe instead of the conversion unit (FRND + F2I); the low bits of the biased sum ARE the integer,
+    // so (bits << 23) is n << 23 (the bias 0x4B400000 has nine zero low bits and shifts out).
+    const float nf = t + 12582912.0f;
+    const float n = nf - 12582912.0f;
     float f = t - n;
     float p = 0.001327647129073739f;
     p = fmaf(p, f, 0.009675540961325169f);
@@ -66,7 +70,7 @@ __device__ __forceinline__ float sas_exp_neg(float x) {
     p = fmaf(p, f, 0.24022120237350464f);
     p = fmaf(p, f, 0.6931469440460205f);
     p = fmaf(p, f, 1.0000001192092896f);
-    return __int_as_float(__float_as_int(p) + (((int)n) << 23));
+    return __int_as_float(__float_as_int(p) + (__float_as_int(nf) << 23));
 }
 
 __device__ __forceinline__ void sas_cp_async16(void *smem_dst, const void *gmem_src) {
@@ -126,11 +130,42 @@ __host__ __device__ __forceinline__ int sas_group_bit(int cx /*0..3*/, int ry /*
     return ((ry >> 1) * 2 + (cx >> 1)) * 4 + (ry & 1) * 2 + (cx & 1);
 }
 
-// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default = all on):
+// Which 4x2-pixel groups a Gaussian's culling extents reach, as inclusive ranges of GLOBAL group
+// columns (4 px wide) and rows (2 px high): column c covers pixel centres 4c+0.5 .. 4c+3.5, so it is
+// reached iff xh >= 4c+0.5 and xl <= 4c+3.5.  (A rounding ulp at an exact boundary is harmless: the
+// extents carry a margin of 0.02 px + 0.1 %, see sas_project.cu project_one.)
+struct SasGroupReach { int cx0, cx1, ry0, ry1; };
+__device__ __forceinline__ SasGroupReach sas_group_reach(const float4 reach) {
+    SasGroupReach g;
+    g.cx0 = (int)ceilf((reach.x - 3.5f) * 0.25f);
+    g.cx1 = (int)floorf((reach.y - 0.5f) * 0.25f);
+    g.ry0 = (int)ceilf((reach.z - 1.5f) * 0.5f);
+    g.ry1 = (int)floorf((reach.w - 0.5f) * 0.5f);
+    return g;
+}
+// ... restricted to tile (tx, ty): 32-bit mask in the layout of sas_common.cuh sas_group_bit.
+__device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, int tx, int ty) {
+    const int c0 = max(g.cx0 - 4 * tx, 0), c1 = min(g.cx1 - 4 * tx, 3);
+    const int r0 = max(g.ry0 - 8 * ty, 0), r1 = min(g.ry1 - 8 * ty, 7);
+    if (c0 > c1 || r0 > r1) return 0u;
+    const unsigned xm = ((2u << (c1 - c0)) - 1u) << c0;  // 4 bits
+    const unsigned ym = ((2u << (r1 - r0)) - 1u) << r0;  // 8 bits
+    const unsigned xs = (xm & 3u) | ((xm & 12u) << 2);   // columns 0,1 -> bits 0,1; columns 2,3 -> bits 4,5
+    // row r -> bit offset (r>>1)*8 + (r&1)*2; the shifted copies of xs never overlap, so multiply = OR of shifts
+    const unsigned e = (ym & 1u) | ((ym & 2u) << 1) | ((ym & 4u) << 6) | ((ym & 8u) << 7) | ((ym & 16u) << 12) | ((ym & 32u) << 13) |
+                       ((ym & 64u) << 18) | ((ym & 128u) << 19);
+    return xs * e;
+}
+
+// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default 0xcf):
 //   bit 0  compositor: per-group (4x2) hit masks instead of one per warp footprint
 //   bit 1  group-level static shortcut (off: every group of a tile with link Gaussians is composited)
 //   bit 2  bucket-sort size classes run on concurrent streams (fork / join on the caller's stream)
 //   bit 3  merge skips tiles whose link bucket is empty (their ids are produced on demand for debug fetches)
+//   bit 6  compositor: each staged record's 32-bit group reach mask is computed once per CTA (by the thread
+//          that staged it) instead of every warp testing every record against its own four groups
+//   bit 7  compositor: warp -> footprint map rotated with the work-item index (evens out the four schedulers)
+//   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
 // Outputs of the compositor: per-image buffers (any may be null) ...
@@ -146,7 +181,17 @@ struct SasViewBuf {
     int *n_contrib;  // [C,H,W]
 };
 
+// Constants of the link-pose algebra (sas_pose.cu); fk_R / fk_t are device pointers [L,9] / [L,3].
+struct SasPoseModel {
+    int L;
+    double s, Ri[9], ti[3], weld_t[3];
+    const double *fk_R, *fk_t;
+};
+
 // Launchers (each returns the cudaError_t of the launch).
+cudaError_t sas_launch_link_poses(const double *body, const SasPoseModel &m, int E, float *out, cudaStream_t st);
+cudaError_t sas_launch_unproject(const float *depth, int I, int W, int H, float fx, float fy, float cx, float cy, float max_depth, float *xyz,
+                                 unsigned char *valid, cudaStream_t st);
 cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C, int I,
                                   int W, int H, int tile_w, int tile_h, SasWork *work, unsigned char *view_tile_needed, int *sort_list,
                                   int *comp_list, cudaStream_t st, int *n_launches);

@@ -33,7 +33,7 @@
 
 namespace {
 
-constexpr int CB = 256;  // Gaussians per batch = threads per CTA
+constexpr int CB = 256;  // threads of the copy kernel = pixels of a tile
 
 __device__ __forceinline__ unsigned char to_u8(float v) {
     v = fminf(fmaxf(v, 0.0f), 1.0f);
@@ -50,7 +50,7 @@ struct Pixel {
 // Blend staged record j into this lane's pixel (gsplat rasterize_to_pixels inner body).
 __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) {
     const float4 A = sb[j].a;
-    const float4 B = sb[j].b;
+    const float2 B = *reinterpret_cast<const float2 *>(&sb[j].b);  // conic c / 2, opacity
     const float dx = A.x - p.pxf, dy = A.y - p.pyf;
     const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
     if (!p.done && sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {
@@ -76,20 +76,34 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
 // Composite the cnt records of one staged batch into this lane's pixel (whole warp calls this).
 // X0, Y0: centre of the first pixel of the warp's 8x4 footprint.
 //
-// GROUPS = false: one hit mask per warp (the 8x4 footprint); every lane walks every hit.
-// GROUPS = true:  the footprint is split into four 4x2 blocks, one per 8-lane group (= one LDS.128
+// MODE 0: one hit mask per warp (the 8x4 footprint); every lane walks every hit.
+// MODE 1: the footprint is split into four 4x2 blocks, one per 8-lane group (= one LDS.128
 //   phase, so the four groups reading four different records costs no extra shared-memory
 //   wavefronts); each group gets its own hit mask from four ballots and walks only its own hits, the
 //   groups diverge inside the 32-record chunk and reconverge after it.  CPU work model
-//   (tools/analyze_composite.py): 66 % of the per-warp walk iterations on the pusht batch.
-template <bool GROUPS>
-__device__ __forceinline__ void process_batch(const SasRecord *sb, int cnt, Pixel &p, float X0, float Y0) {
+//   (tools/analyze_composite.py): 66 % of the per-warp walk iterations on the pusht batch; measured
+//   18.1 M -> 10.1 M walk iterations per launch together with the static groups.
+// MODE 2: as MODE 1, but the hit test is not repeated by every warp: the thread that staged a record
+//   computed its 32-bit reach mask over all the tile's groups once (s_reach), a warp just ballots its
+//   own four bits (profile of MODE 1: 60 instructions per 32-record chunk per warp in the test phase,
+//   18 % of the kernel's instructions).
+template <int MODE>
+__device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigned *s_reach, int warp, int cnt, Pixel &p, float X0, float Y0) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3;
     for (int j0 = 0; j0 < cnt; j0 += 32) {
         const unsigned dm = __ballot_sync(0xffffffffu, p.done);
         if (dm == 0xffffffffu) break;
-        if (GROUPS) {
+        unsigned mask;
+        if (MODE == 2) {
+            const unsigned bits = (j0 + lane < cnt ? s_reach[j0 + lane] : 0u) >> (warp * 4);
+            const unsigned b00 = __ballot_sync(0xffffffffu, bits & 1u);
+            const unsigned b10 = __ballot_sync(0xffffffffu, bits & 2u);
+            const unsigned b01 = __ballot_sync(0xffffffffu, bits & 4u);
+            const unsigned b11 = __ballot_sync(0xffffffffu, bits & 8u);
+            mask = (grp & 2) ? ((grp & 1) ? b11 : b01) : ((grp & 1) ? b10 : b00);
+            if (((dm >> (grp * 8)) & 0xffu) == 0xffu) mask = 0u;  // every pixel of this group has finished
+        } else if (MODE == 1) {
             bool hx0 = false, hx1 = false, hy0 = false, hy1 = false;
             if (j0 + lane < cnt) {
                 const float4 A = sb[j0 + lane].a;
@@ -104,14 +118,8 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, int cnt, Pixe
             const unsigned b10 = __ballot_sync(0xffffffffu, hx1 && hy0);
             const unsigned b01 = __ballot_sync(0xffffffffu, hx0 && hy1);
             const unsigned b11 = __ballot_sync(0xffffffffu, hx1 && hy1);
-            unsigned mask = (grp & 2) ? ((grp & 1) ? b11 : b01) : ((grp & 1) ? b10 : b00);
+            mask = (grp & 2) ? ((grp & 1) ? b11 : b01) : ((grp & 1) ? b10 : b00);
             if (((dm >> (grp * 8)) & 0xffu) == 0xffu) mask = 0u;  // every pixel of this group has finished
-            while (mask) {  // groups diverge here; no warp-synchronous operation inside
-                const int j = j0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                blend_one(sb, j, p);
-            }
-            __syncwarp();
         } else {
             bool hit = false;
             if (j0 + lane < cnt) {
@@ -119,13 +127,15 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, int cnt, Pixe
                 const float4 B = sb[j0 + lane].b;
                 hit = (A.x + B.z >= X0) && (A.x - B.z <= X0 + 7.0f) && (A.y + B.w >= Y0) && (A.y - B.w <= Y0 + 3.0f);
             }
-            unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int j = j0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                blend_one(sb, j, p);
-            }
+            mask = __ballot_sync(0xffffffffu, hit);
         }
+        const SasRecord *sb1 = sb + j0 - 1;  // __ffs is one-based
+        while (mask) {  // the groups diverge here; no warp-synchronous operation inside
+            const int j = __ffs(mask);
+            mask &= mask - 1;
+            blend_one(sb1, j, p);
+        }
+        __syncwarp();
     }
 }
 
@@ -143,16 +153,27 @@ __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *sr
     sas_cp_async16(&dst->c, &src->c);
 }
 
-template <int MIN_CTAS, bool GROUPS>
-__global__ void __launch_bounds__(CB, MIN_CTAS)
+// WARPS = warps per CTA = 8 (one CTA per tile), 4 or 2: a tile is cut into 8 / WARPS horizontal strips,
+// each composited by its own CTA with its own staging pipeline (batches of WARPS * 32 records) and its
+// own early exit.  Why: per batch a CTA waits for its slowest warp, and the slowest warp is the one
+// over the densest 4x2 block (CPU work model tools/analyze_balance.py: the other warps wait 51 % of the
+// time, whatever the block -> warp assignment) -- so what keeps the schedulers fed is the NUMBER of
+// independent CTAs resident on the SM, not the warps of one CTA.
+__constant__ int sas_variant_flags_dev = 0xff;
+
+template <int WARPS, int MODE>
+__global__ void __launch_bounds__(WARPS * 32, 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
                  const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_list, SasWork *work, int n_bg, int n_dyn,
                  int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters) {
-    __shared__ SasRecord stage[2][CB];
+    constexpr int NT = WARPS * 32;     // threads = records per batch
+    constexpr int PARTS = 8 / WARPS;   // CTAs per tile
+    __shared__ SasRecord stage[2][NT];
+    __shared__ unsigned s_reach[MODE == 2 ? 2 : 1][MODE == 2 ? NT : 1];
     __shared__ unsigned s_take;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int T = tile_w * tile_h;
     const long long IT = (long long)I * T;
     int staged = 0;
@@ -162,8 +183,14 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         if (tid == 0) s_take = atomicAdd(&work->comp_take, 1u);
         __syncthreads();
         const unsigned k = s_take;
-        if (k >= work->comp_total) break;
-        const long long item = comp_list[k];
+        if (k >= work->comp_total * PARTS) break;
+        const long long item = comp_list[k / PARTS];
+        // Which 8x4 footprint of the tile this warp composites.  Hardware warp w of every resident CTA issues
+        // from scheduler w % 4, and the background makes the same footprint of the same tile heavy in every
+        // image of a view, so a fixed warp -> footprint map loads the four schedulers unevenly (profile: 0.90 M
+        // to 1.35 M instructions per scheduler); rotating it with the work-item index evens that out.
+        const int rot = (sas_variant_flags_dev & 128) ? (int)((k / PARTS) & 7u) : 0;
+        const int warp = (((int)(k % PARTS) * WARPS + (tid >> 5)) + rot) & 7;
 
         // ---- resolve the item: id list (base, stride), record bases, output image ----
         const bool is_view = item >= IT;
@@ -217,26 +244,35 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         p.done = !inside || group_static;
 
         // ---- batches: prologue puts batch 0 in flight and the id of batch 1 in a register ----
-        const int nb = (n + CB - 1) / CB;
+        const int nb = (n + NT - 1) / NT;
         int gid_next = 0;
         if (tid < n) stage_record(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)));
         sas_cp_async_commit();
-        if (CB + tid < n) gid_next = __ldg(gids + (size_t)(CB + tid) * gstride);
+        if (NT + tid < n) gid_next = __ldg(gids + (size_t)(NT + tid) * gstride);
         for (int b = 0; b < nb; b++) {
             sas_cp_async_wait<0>();
-            if (__syncthreads_count(p.done) == CB) break;  // also publishes batch b to the CTA
-            const int cnt = min(CB, n - b * CB);
+            if (MODE == 2) {  // this thread's record of batch b has landed: which of the tile's 32 groups can it reach
+                unsigned m = 0u;
+                if (b * NT + tid < n) {
+                    const float4 A = stage[b & 1][tid].a;
+                    const float4 B = stage[b & 1][tid].b;
+                    m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+                }
+                s_reach[b & 1][tid] = m;
+            }
+            if (__syncthreads_count(p.done) == NT) break;  // also publishes batch b (records and reach masks) to the CTA
+            const int cnt = min(NT, n - b * NT);
             staged += cnt;
             const int buf = b & 1;
             {  // batch b+1 -> other buffer; id of batch b+2 -> register
-                const int e1 = (b + 1) * CB + tid;
+                const int e1 = (b + 1) * NT + tid;
                 if (e1 < n) stage_record(&stage[buf ^ 1][tid], SAS_REC_OF(gid_next));
                 sas_cp_async_commit();
-                const int e2 = e1 + CB;
+                const int e2 = e1 + NT;
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
             if (__all_sync(0xffffffffu, p.done)) continue;  // whole warp finished: only keep feeding the pipeline
-            process_batch<GROUPS>(stage[buf], cnt, p, X0, Y0);
+            process_batch<MODE>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp, cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
 #undef SAS_REC_OF
@@ -255,7 +291,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             }
         }
     }
-    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged);
+    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged * WARPS);  // in eighths of a tile
 }
 
 // Images whose link bucket for a tile is empty take the tile from their view's buffers; the
@@ -322,8 +358,8 @@ cudaError_t sas_composite_init(int n_sms) {
     return cudaSuccess;
 }
 
-// Registers are capped for 8 resident CTAs/SM (measured 4.5 % faster than 6).  SAS_VARIANT bit 0
-// (sas_common.cuh) selects the per-group hit masks.
+// Registers are capped at 32 so that 64 warps stay resident per SM (measured 4.5 % faster than 48).
+// SAS_VARIANT (sas_common.cuh): bit 0 per-group hit masks, bits 4-5 CTAs per tile.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
                                  const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
@@ -332,8 +368,24 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  int *n_launches) {
 #define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
-    if (sas_variant_flags() & 1) composite_kernel<8, true><<<g_comp_sms * 8, CB, 0, st>>>(SAS_ARGS);
-    else composite_kernel<8, false><<<g_comp_sms * 8, CB, 0, st>>>(SAS_ARGS);
+    const int vf = sas_variant_flags();
+    static bool flags_uploaded = false;
+    if (!flags_uploaded) {
+        cudaError_t e = cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
+        if (e != cudaSuccess) return e;
+        flags_uploaded = true;
+    }
+    const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
+#define SAS_COMP(W, M) composite_kernel<W, M><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
+    const int mode = (vf & 1) ? ((vf & 64) ? 2 : 1) : 0;
+    if (parts == 0) {
+        if (mode == 2) SAS_COMP(8, 2); else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
+    } else if (parts == 1) {
+        if (mode == 2) SAS_COMP(4, 2); else SAS_COMP(4, 1);
+    } else {
+        if (mode == 2) SAS_COMP(2, 2); else SAS_COMP(2, 1);
+    }
+#undef SAS_COMP
 #undef SAS_ARGS
     dim3 grid(tile_w * tile_h, I);
     copy_static_tiles_kernel<<<grid, CB, 0, st>>>(row_tile_count, view_of_image, tile_dyn_mask, C, W, H, tile_w, tile_h, bg0, bg1, bg2, img_out,

@@ -213,28 +213,6 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
     return true;
 }
 
-// Which 4x2-pixel groups of the tile at pixel origin (tx0, ty0) the Gaussian's culling extents reach
-// (bit layout: sas_common.cuh sas_group_bit).  Same comparisons as the compositor's per-group test.
-__device__ __forceinline__ unsigned group_reach_mask(const float4 reach, int tx0, int ty0) {
-    unsigned xm = 0u, ym = 0u;
-#pragma unroll
-    for (int cx = 0; cx < 4; cx++) {
-        const float c0 = (float)(tx0 + 4 * cx) + 0.5f;
-        if (reach.y >= c0 && reach.x <= c0 + 3.0f) xm |= 1u << cx;
-    }
-#pragma unroll
-    for (int ry = 0; ry < 8; ry++) {
-        const float r0 = (float)(ty0 + 2 * ry) + 0.5f;
-        if (reach.w >= r0 && reach.z <= r0 + 1.0f) ym |= 1u << ry;
-    }
-    const unsigned xs = (xm & 3u) | (((xm >> 2) & 3u) << 4);  // columns 0,1 -> bits 0,1; columns 2,3 -> bits 4,5
-    unsigned m = 0u;
-#pragma unroll
-    for (int ry = 0; ry < 8; ry++)
-        if ((ym >> ry) & 1u) m |= xs << ((ry >> 1) * 8 + (ry & 1) * 2);
-    return m;
-}
-
 constexpr int PROJ_FAST_TILES = 4;  // Gaussians covering at most this many tiles count through shared memory
 
 // One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
@@ -270,13 +248,13 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
     if (vis) {
         const int ntile = (x1 - x0) * (y1 - y0);
         const bool fast = smem_tiles && ntile <= PROJ_FAST_TILES;
+        const SasGroupReach gr = sas_group_reach(reach);
         for (int y = y0; y < y1; y++)
             for (int x = x0; x < x1; x++) {
                 const int t = y * tile_w + x;
-                atomicAdd((fast ? s_cnt : tc) + t, 1u);
+                if (fast) atomicAdd(s_cnt + t, 1u); else atomicAdd(tc + t, 1u);
                 if (dm) {
-                    // screen-filling Gaussians: call every group reachable instead of testing hundreds of tiles
-                    const unsigned m = ntile <= 64 ? group_reach_mask(reach, x * SAS_TILE_PX, y * SAS_TILE_PX) : 0xffffffffu;
+                    const unsigned m = sas_group_reach_mask(gr, x, y);
                     // read first: after the first few Gaussians of a CTA the bits are already set
                     if (smem_masks) {
                         if ((s_mask[t] & m) != m) atomicOr(s_mask + t, m);

@@ -3,7 +3,8 @@ reference's single-env wrapper (the reference renders one camera of one env per 
 /root/reference/sim_a_splat/env/splat/splat_env_wrapper.py:147-158).
 
 One `VecSplatRenderer.render(draw_msgs)` call = one pass of the hot path over E x C images: the per-env link
-poses come from `SplatHandler.link_poses_from_msg` (the draw_handler algebra), fixed cameras are shared
+poses are composed on the device from the draw messages' body poses (the draw_handler algebra,
+`sas_set_link_poses_from_bodies`), fixed cameras are shared
 views, link-attached cameras get one view per env.  Observations keep the reference layout: `camera_{i}`
 = uint8 [E,3,H,W] (splat_env_wrapper.py:132-138).
 """
@@ -37,14 +38,16 @@ class VecSplatRenderer:
                                       max_height=self.H, max_isects=max_isects)
         fy = self.H / (2.0 * np.tan(fov / 2.0))
         self.K = np.array([[fy, 0, self.W / 2.0], [0, fy, self.H / 2.0], [0, 0, 1.0]])
+        if self.renderer.L:
+            self.renderer.set_pose_model(**handler.pose_model())  # link poses are composed on the device from body poses
         self._fixed_vm = [c2w_opencv_to_viewmat(v["local_frame"].rotation().wxyz, v["local_frame"].translation()) for v in self.fixed.values()]
         self._static_cameras_set = False
 
     def render(self, draw_msgs: Sequence, outputs=("rgb_u8",), to_host: bool = True) -> Dict[str, np.ndarray]:
         assert len(draw_msgs) == self.E
-        poses = np.stack([self.handler.link_poses_from_msg(m) for m in draw_msgs])  # [E,L,12]
         r = self.renderer
-        r.set_link_poses(poses)
+        if r.L:  # draw_handler's algebra runs on the device over all (env, link) at once (csrc/sas_pose.cu)
+            r.set_link_poses_from_bodies(np.stack([self.handler.body_poses_from_msg(m) for m in draw_msgs]))  # [E,L,7] fp64
         if self.moving or not self._static_cameras_set:
             vms, env = [], []
             for e, msg in enumerate(draw_msgs):

@@ -69,3 +69,13 @@ class GaussianSplat:
         out = r.render(("rgb", "depth", "alpha"), background=self.background, nerfstudio_post=True)
         return {"rgb": out["rgb"][0], "depth": out["depth"][0][..., None], "accumulation": out["alpha"][0][..., None],
                 "background": torch.tensor(self.background, device=out["rgb"].device)}
+
+    def generate_RGBD_point_cloud(self, pose, max_depth: float = 1.0, return_pcd: bool = False):
+        """Render at `pose` and unproject every pixel with depth < max_depth through the pinhole model of the
+        reference (nerfstudio_utils.py:375-472; the arithmetic is :441-452): returns (points [M,3] in the CAMERA
+        frame with OpenCV axes, colours [M,3], depth image [H,W], rgb image [H,W,3]).  The open3d point-cloud
+        object, outlier removal and world transform of the reference are not reproduced."""
+        out = self.render(pose)
+        depth = out["depth"][..., 0]
+        xyz, valid = self._renderer.unproject_depth(depth[None], self.K, max_depth)
+        return xyz[0][valid[0]], out["rgb"][valid[0]], depth, out["rgb"]

@@ -83,6 +83,49 @@ class SplatRenderer:
             code = self._lib.sas_set_link_poses(self._h, p.ctypes.data, p.shape[0], L.SAS_MEM_HOST, self._stream(stream))
         L.check(self._lib, self._h, code)
 
+    def set_pose_model(self, scale: float, Ri, ti, weld_t, fk_R, fk_t) -> None:
+        """Constants of the reference's link-pose algebra (splat_handler.py:62-83, :158-163, :229-235): after this,
+        set_link_poses_from_bodies() composes rot / pos on the device (csrc/sas_pose.cu)."""
+        fkR = np.ascontiguousarray(fk_R, dtype=np.float64).reshape(self.L, 9)
+        fkt = np.ascontiguousarray(fk_t, dtype=np.float64).reshape(self.L, 3)
+        m = L.PoseModel()
+        m.n_links, m.scale = self.L, float(scale)
+        m.Ri = (C.c_double * 9)(*np.asarray(Ri, dtype=np.float64).reshape(9))
+        m.ti = (C.c_double * 3)(*np.asarray(ti, dtype=np.float64).reshape(3))
+        m.weld_t = (C.c_double * 3)(*np.asarray(weld_t, dtype=np.float64).reshape(3))
+        m.fk_R, m.fk_t = fkR.ctypes.data, fkt.ctypes.data
+        L.check(self._lib, self._h, self._lib.sas_set_pose_model(self._h, C.byref(m)))
+
+    def set_link_poses_from_bodies(self, body_wxyz_xyz, stream=None) -> None:
+        """body_wxyz_xyz [E,L,7] fp64: the draw message's (quaternion wxyz, position) of the L robot bodies that
+        drive the link groups (manipulator_env.py:377-390), numpy (host) or a CUDA float64 tensor."""
+        torch = self._torch
+        if isinstance(body_wxyz_xyz, torch.Tensor) and body_wxyz_xyz.is_cuda:
+            b = body_wxyz_xyz.contiguous().double()
+            code = self._lib.sas_set_link_poses_from_bodies(self._h, C.c_void_p(b.data_ptr()), b.numel() // (self.L * 7), L.SAS_MEM_DEVICE,
+                                                            self._stream(stream))
+            self._keep_bodies = b
+        else:
+            b = np.ascontiguousarray(body_wxyz_xyz, dtype=np.float64).reshape(-1, self.L, 7)
+            code = self._lib.sas_set_link_poses_from_bodies(self._h, b.ctypes.data, b.shape[0], L.SAS_MEM_HOST, self._stream(stream))
+        L.check(self._lib, self._h, code)
+
+    def unproject_depth(self, depth, K, max_depth: float = 1e10, stream=None):
+        """Pinhole unprojection of nerfstudio_utils.py:441-452 on the device: depth [I,H,W] (CUDA float32 tensor) ->
+        (xyz [I,H,W,3] camera-frame points, valid [I,H,W] bool = depth < max_depth)."""
+        torch = self._torch
+        d = depth.contiguous().float()
+        if d.dim() == 2:
+            d = d[None]
+        I, H, W = d.shape
+        xyz = torch.empty((I, H, W, 3), dtype=torch.float32, device=d.device)
+        valid = torch.empty((I, H, W), dtype=torch.uint8, device=d.device)
+        Kf = _f32c(K).reshape(9)
+        L.check(self._lib, self._h, self._lib.sas_unproject_depth(self._h, C.c_void_p(d.data_ptr()), I, W, H, Kf.ctypes.data, float(max_depth),
+                                                                  C.c_void_p(xyz.data_ptr()), C.c_void_p(valid.data_ptr()), L.SAS_MEM_DEVICE,
+                                                                  self._stream(stream)))
+        return xyz, valid.bool()
+
     def set_cameras(self, viewmats, Ks, width: int, height: int, env_of_image: Optional[Sequence[int]] = None, stream=None) -> None:
         """viewmats [I,4,4] world->camera (OpenCV axes), Ks [I,3,3] or [3,3]; host arrays."""
         vm = _f32c(viewmats).reshape(-1, 16)
@@ -165,6 +208,12 @@ class SplatRenderer:
 
     def last_launch_count(self) -> int:
         return int(self._lib.sas_last_launch_count(self._h))
+
+    def link_poses(self, n_envs: int) -> np.ndarray:
+        """[n_envs, L, 12] fp32 link poses currently in effect on the device (parity tests)."""
+        out = np.empty((n_envs, self.L, 12), dtype=np.float32)
+        L.check(self._lib, self._h, self._lib.sas_debug_fetch(self._h, L.SAS_DBG_LINK_POSES, out.ctypes.data, out.nbytes))
+        return out
 
     # -- parity-test access to intermediates ------------------------------------------------
     def debug_intermediates(self) -> dict:

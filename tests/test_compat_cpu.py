@@ -173,6 +173,30 @@ def test_handler_draw_handler_matches_pose_oracle(toy):
     assert not np.allclose(P0[2], ident, atol=1e-3)
 
 
+def test_body_pose_block_reproduces_link_poses_through_the_oracle(toy):
+    """What the device-side pose composition is fed: [L,7] body poses + the pose model; pushed through the fp64
+    oracle they give the same [L,12] block as the host path."""
+    weld = RigidTransformLite(translation=(0.05, -0.02, 0.01))
+    h = _handler(toy, sim_robot_weld_frame_transform=weld)
+    env = FakeManipulatorEnv(toy, seed=9)
+    env.reset(seed=9)
+    msg = env._generate_draw_msg()
+    B, m = h.body_poses_from_msg(msg), h.pose_model()
+    assert B.shape == (N_LINKS, 7) and B.dtype == np.float64 and m["fk_R"].shape == (N_LINKS, 3, 3) and m["fk_t"].shape == (N_LINKS, 3)
+    rows = []
+    for l in range(N_LINKS):
+        rot, pos = po.link_transform(B[l, :4], B[l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+        rows.append(po.poses_to_rot12(rot, pos))
+    np.testing.assert_allclose(np.stack(rows), h.link_poses_from_msg(msg), atol=2e-7)
+    # a message without robot bodies leaves every link at its capture-time pose = identity transform
+    empty = type("M", (), dict(num_links=0, robot_num=[], quaternion=[], position=[], link_name=[]))()
+    B0 = h.body_poses_from_msg(empty)
+    for l in range(N_LINKS):
+        rot, pos = po.link_transform(B0[l, :4], B0[l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+        np.testing.assert_allclose(rot, np.eye(3), atol=1e-12)
+        np.testing.assert_allclose(pos, 0.0, atol=1e-12)
+
+
 def test_handler_rejects_rotated_weld_and_attached_frame_quirk(toy):
     h = _handler(toy, sim_robot_weld_frame_transform=RigidTransformLite(wxyz=(0.0, 1.0, 0.0, 0.0)))
     env = FakeManipulatorEnv(toy)

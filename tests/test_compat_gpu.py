@@ -107,6 +107,58 @@ def test_vec_renderer_matches_single_env_wrappers(toy):
     env.close()
 
 
+def test_device_pose_composition_matches_pose_oracle(toy, assets):
+    """sas_set_link_poses_from_bodies (csrc/sas_pose.cu) == oracle/pose_oracle.py:link_transform (pinned to the
+    reference's draw_handler by tests/golden/draw_handler.npz), over many envs, incl. un-normalised quaternions."""
+    from oracle import pose_oracle as po
+    from sim_a_splat_b200.renderer import SplatRenderer
+    from sim_a_splat_b200.splat.splat_handler import RigidTransformLite, SplatHandler
+
+    h = SplatHandler(toy["root"], toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"],
+                     task_assets_name="tblock_paper.obj", sim_robot_weld_frame_transform=RigidTransformLite(translation=(0.03, 0.01, -0.02)))
+    sc = h.server.build_scene()
+    E = 37
+    r = SplatRenderer(sc, max_images=E, max_envs=E, max_width=64, max_height=64)
+    m = h.pose_model()
+    r.set_pose_model(**m)
+    rng = np.random.default_rng(5)
+    body = np.concatenate([rng.normal(size=(E, N_LINKS, 4)) * rng.uniform(0.2, 3.0, size=(E, N_LINKS, 1)), rng.uniform(-0.6, 0.6, size=(E, N_LINKS, 3))], axis=-1)
+    r.set_link_poses_from_bodies(body)
+    got = r.link_poses(E)
+    want = np.empty_like(got)
+    for e in range(E):
+        for l in range(N_LINKS):
+            rot, pos = po.link_transform(body[e, l, :4], body[e, l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+            want[e, l] = po.poses_to_rot12(rot, pos)
+    np.testing.assert_allclose(got, want, atol=3e-7, rtol=0)
+    # device-resident input gives the same block
+    r.set_link_poses_from_bodies(torch.from_numpy(body).cuda())
+    np.testing.assert_array_equal(r.link_poses(E), got)
+    with pytest.raises(Exception, match="max_envs"):
+        r.set_link_poses_from_bodies(np.zeros((E + 1, N_LINKS, 7)))
+    r.close()
+
+
+def test_unproject_depth_is_the_reference_pinhole_formula():
+    """nerfstudio_utils.py:441-452: x=(u-cx)d/fx, y=(v-cy)d/fy, z=d; mask d<max_depth (bit-exact in fp32)."""
+    from sim_a_splat_b200.renderer import SplatRenderer
+
+    sc = S.make_synthetic_scene(2000, 1, seed=3)
+    H, W = 37, 50
+    K = np.float32([[61.5, 0, 24.25], [0, 60.25, 18.5], [0, 0, 1]])
+    r = SplatRenderer(sc, max_images=2, max_width=W, max_height=H)
+    r.set_cameras(S.ring_cameras(2, (0, 0, 0), seed=1), K, W, H)
+    depth = r.render(("depth",))["depth"]
+    xyz, valid = r.unproject_depth(depth, K, max_depth=1.1)
+    d = depth.cpu().numpy()
+    u, v = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    want = np.stack([(u - K[0, 2]) * d / K[0, 0], (v - K[1, 2]) * d / K[1, 1], d], axis=-1).astype(np.float32)
+    np.testing.assert_array_equal(xyz.cpu().numpy(), want)
+    np.testing.assert_array_equal(valid.cpu().numpy(), d < np.float32(1.1))
+    assert 0 < int(valid.sum()) < valid.numel()
+    r.close()
+
+
 def test_gaussian_splat_render_contract(toy, assets):
     """GaussianSplat.render(pose) (nerfstudio_utils.py:123-177): OpenGL c2w in, splatfacto output dict out."""
     from pathlib import Path
@@ -127,17 +179,21 @@ def test_gaussian_splat_render_contract(toy, assets):
     np.testing.assert_allclose(vm[0], np.linalg.inv(c2w_cv), atol=1e-5)
     ref = oracle.render(sc.as_oracle_dict(), vm, K[None], W, H)
     ns = oracle.oracle.nerfstudio_outputs(ref, NS_BACKGROUND)
-    assert np.abs(out["rgb"].cpu().numpy() - ns["rgb"]).max() <= 1e-3
-    assert np.abs(out["depth"].cpu().numpy() - ns["depth"]).max() <= 1e-3
-    np.testing.assert_array_equal(out["accumulation"].cpu().numpy()[..., 0], ref["alpha"])
+    assert np.abs(out["rgb"].cpu().numpy() - ns["rgb"][0]).max() <= 1e-3
+    assert np.abs(out["depth"].cpu().numpy() - ns["depth"][0]).max() <= 1e-3
+    np.testing.assert_array_equal(out["accumulation"].cpu().numpy()[..., 0], ref["alpha"][0])
     assert float(out["rgb"].min()) >= 0.0 and float(out["rgb"].max()) <= 1.0
     # depth convention of generate_RGBD_point_cloud (:441-452): z along the optical axis -> unprojected points
     # of opaque pixels lie in front of the camera within the scene bounds
     d = out["depth"].cpu().numpy()[..., 0]
-    a = ref["alpha"]
+    a = ref["alpha"][0]
     assert np.all(d[a > 0.99] > 0.3) and np.all(d[a > 0.99] < 4.0)
     # res_factor rescales intrinsics and size (Cameras.rescale_output_resolution, :99-100)
     half = GaussianSplat(sc, res_factor=0.5, intrinsics=(H, W, K))
     assert half.get_camera_intrinsics()[:2] == (H // 2, W // 2)
     o2 = half.render(c2w_gl[:3])
     assert o2["rgb"].shape == (H // 2, W // 2, 3)
+    pts, cols, dimg, rgbimg = gs.generate_RGBD_point_cloud(torch.from_numpy(c2w_gl[:3]).float(), max_depth=1.5)
+    n_valid = int((d < 1.5).sum())
+    assert pts.shape == (n_valid, 3) and cols.shape == (n_valid, 3) and 0 < n_valid < H * W
+    assert float(pts[:, 2].max()) < 1.5 and torch.equal(dimg, out["depth"][..., 0])

@@ -1,0 +1,141 @@
+"""BASELINE.json configs at (or near) full size on the GPU.  Image-for-image oracle checks on what the CPU
+oracle finishes in seconds; size-independent properties (determinism, env-shard invariance, camera-chunk
+invariance, identical env state -> identical image) for the rest.  Also the tile-count regimes of the
+projection / emission kernels (shared-memory histograms, no shared-memory masks, global atomics)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from sim_a_splat_b200 import dist as D
+from sim_a_splat_b200 import scene as S
+from sim_a_splat_b200.renderer import SplatRenderer
+
+from parity_utils import assert_parity, compare, run_both
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("rgb", "depth", "alpha", "n_contrib")
+
+
+def _check_against_oracle(sc, got, vms, K, W, H, poses, env, pick):
+    ref = oracle.render(sc.as_oracle_dict(), vms[pick], np.repeat(K[None], len(pick), 0), W, H, poses, env[pick],
+                        keep={"rgb", "depth", "alpha", "n_contrib"})
+    for k in NAMES:
+        g = got[k][pick].cpu().numpy()
+        if k == "n_contrib":
+            np.testing.assert_array_equal(g, ref[k])
+        else:
+            assert np.abs(g - ref[k]).max() <= 1e-3, k
+
+
+def test_config3_xarm_four_cameras_720p_full(assets):
+    """configs[2] in full: real xarm6-1 masks (L=7), 4 cameras x 1280x720 RGB + depth, one env."""
+    sc = S.make_reference_like_scene("robots-scene-v2", 3, 103, assets=assets)
+    cen = sc.means[sc.link_id >= 0].mean(0)
+    W, H = 1280, 720
+    vms, K = S.ring_cameras(4, cen, 9), S.fov_intrinsics(W, H)
+    poses = S.random_link_poses(1, 7, 2000)
+    r = SplatRenderer(sc, max_images=4, max_envs=1, max_width=W, max_height=H)
+    r.set_link_poses(poses)
+    r.set_cameras(vms, K, W, H, np.zeros(4, np.int32))
+    a = {k: v.clone() for k, v in r.render(NAMES).items()}
+    st = r.stats()
+    assert st["overflow"] == 0 and st["n_views"] == 4 and st["tile_w"] * st["tile_h"] == 3600
+    b = r.render(NAMES)
+    for k in NAMES:
+        assert torch.equal(a[k], b[k]), k
+    _check_against_oracle(sc, a, vms, K, W, H, poses, np.zeros(4, np.int32), [1, 3])
+    # camera-chunk invariance: the same cameras rendered two at a time give the same images
+    for c0 in (0, 2):
+        r.set_cameras(vms[c0:c0 + 2], K, W, H, np.zeros(2, np.int32))
+        part = r.render(NAMES)
+        for k in NAMES:
+            assert torch.equal(part[k], a[k][c0:c0 + 2]), (k, c0)
+    r.close()
+
+
+def test_config4_divar_one_gpu_shard_full(assets):
+    """configs[3], the shard one of 8 GPUs renders: divar113vhw (N=298 588 canonical, L=6), 256 envs x 2 fixed
+    cameras at 224x224 = 512 images, 2 shared views."""
+    sc = S.make_reference_like_scene("divar113vhw", 3, 104, assets=assets)
+    cen = sc.means[sc.link_id >= 0].mean(0)
+    W, H, E_total, G = 224, 224, 2048, 8
+    envs = D.shard_envs(E_total, G, 3)
+    E = len(envs)
+    assert E == 256
+    cams, K = S.ring_cameras(2, cen, 10), S.fov_intrinsics(W, H)
+    poses = S.random_link_poses(E_total, 6, 3000)[envs.start:envs.stop]
+    poses[9] = poses[130]
+    vms = np.tile(cams, (E, 1, 1))
+    env = np.repeat(np.arange(E, dtype=np.int32), 2)
+    r = SplatRenderer(sc, max_images=2 * E, max_envs=E, max_width=W, max_height=H, max_isects=120_000_000)
+    r.set_link_poses(poses)
+    r.set_cameras(vms, K, W, H, env)
+    a = {k: v.clone() for k, v in r.render(NAMES).items()}
+    st = r.stats()
+    assert st["overflow"] == 0 and st["n_views"] == 2 and st["n_images"] == 512
+    b = r.render(NAMES)
+    for k in NAMES:
+        assert torch.equal(a[k], b[k]), k                       # deterministic
+        assert torch.equal(a[k][18:20], a[k][260:262]), k       # env 9 == env 130 (both cameras)
+    _check_against_oracle(sc, a, vms, K, W, H, poses, env, [0, 19, 261, 511])
+    # shard invariance: a rank that renders only envs [64, 96) produces the same images
+    sub = slice(64, 96)
+    r.set_link_poses(poses[sub])
+    r.set_cameras(vms[2 * 64:2 * 96], K, W, H, env[:64])
+    part = r.render(NAMES)
+    for k in NAMES:
+        assert torch.equal(part[k], a[k][2 * 64:2 * 96]), k
+    r.close()
+
+
+def test_config5_scaled_sort_composite_stress():
+    """configs[4] scaled to what the oracle checks in seconds: 250 k Gaussians, SH-3, 1920x1080 (8160 tiles:
+    shared-memory tile counters but global group masks), 2 cameras, 3 % of the Gaussians on 7 links."""
+    sc = S.make_synthetic_scene(250_000, 3, seed=105, link_counts=(1500, 1300, 1200, 1100, 1000, 900, 500))
+    W, H = 1920, 1080
+    vms, K = S.ring_cameras(2, (0, 0, 0), seed=12), S.fov_intrinsics(W, H)
+    poses = S.random_link_poses(1, 7, 4000)
+    gpu, ref = run_both(sc, vms, K[None], W, H, poses, [0, 0], max_isects=40_000_000)
+    rep = compare(gpu, ref)
+    print(rep)
+    assert_parity(rep)
+    assert rep["M_ref"] > 3_000_000
+
+
+def test_more_than_8192_tiles_uses_global_counters():
+    """2064x1104 -> 129 x 69 = 8901 tiles: beyond the shared-memory histograms of projection / emission."""
+    sc = S.make_synthetic_scene(12_000, 2, seed=23, link_counts=(600, 300))
+    W, H = 2064, 1104
+    gpu, ref = run_both(sc, S.ring_cameras(1, (0, 0, 0), seed=4), S.fov_intrinsics(W, H)[None], W, H, S.random_link_poses(1, 2, 50), [0])
+    assert gpu["stats"]["tile_w"] * gpu["stats"]["tile_h"] == 8901
+    rep = compare(gpu, ref)
+    print(rep)
+    assert_parity(rep)
+
+
+@pytest.mark.parametrize("n_million", [1.5, 6.0])
+def test_config5_large_scene_properties(n_million):
+    """configs[4] regime without an oracle: millions of Gaussians at 1080p.  Camera-chunk invariance (cameras
+    are the most significant key field, so chunks must reproduce the one-call images bit for bit),
+    determinism, and the overflow path at scale."""
+    N = int(n_million * 1e6)
+    sc = S.make_synthetic_scene(N, 3, seed=106)
+    W, H = 1920, 1080
+    vms, K = S.ring_cameras(4, (0, 0, 0), seed=13), S.fov_intrinsics(W, H)
+    r = SplatRenderer(sc, max_images=4, max_width=W, max_height=H, max_isects=8_000_000)
+    r.set_cameras(vms, K, W, H)
+    a = {k: v.clone() for k, v in r.render(NAMES, check=True).items()}   # grows the intersection buffers once
+    st = r.stats()
+    assert st["overflow"] == 0 and st["n_isects"] > 8_000_000 and st["n_visible_src"] > N
+    b = r.render(NAMES)
+    for k in NAMES:
+        assert torch.equal(a[k], b[k]), k
+    r.set_cameras(vms[1:3], K, W, H)
+    part = r.render(NAMES)
+    for k in NAMES:
+        assert torch.equal(part[k], a[k][1:3]), k
+    assert float(a["alpha"].max()) <= 1.0 and float(a["alpha"].min()) >= 0.0
+    assert int(a["n_contrib"].max()) > 50
+    r.close()
