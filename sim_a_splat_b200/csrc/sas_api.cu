@@ -56,6 +56,19 @@ struct sas_renderer {
     int last_launches = 0;
     bool stage_timing = false;
     cudaEvent_t stage_ev[SAS_N_STAGES + 1] = {};
+    // CUDA graph of the device work of one sas_render (captured on first use, replayed while the key matches)
+    struct GraphKey {
+        int I, C, W, H, ns, flags;
+        float bg[3];
+        void *rgb, *depth, *alpha, *u8, *nc;
+        long long max_isects;
+        unsigned long long buf_gen;
+    };
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key{};
+    int graph_launches = 0;
+    unsigned long long buf_gen = 0;  // bumped whenever a work buffer is (re)allocated: invalidates the graph
+    int graph_mode = -1;             // SAS_GRAPH environment variable (default on)
 };
 
 namespace {
@@ -85,6 +98,7 @@ int ensure(sas_renderer *r, DevBuf &b, size_t bytes) {
     if (bytes == 0) bytes = 16;
     SAS_CUDA(r, cudaMalloc(&b.p, bytes));
     b.bytes = bytes;
+    r->buf_gen++;
     return SAS_OK;
 }
 
@@ -249,6 +263,7 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : r->fork_ev)
         if (ev) cudaEventDestroy(ev);
+    if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
     for (cudaStream_t s : r->aux)
         if (s) cudaStreamDestroy(s);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
@@ -417,33 +432,14 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     return SAS_OK;
 }
 
-int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
-    if (!r || !out) return SAS_EINVAL;
-    if (!r->cameras_set) return fail(r, SAS_ESTATE, "sas_render: sas_set_cameras has not been called");
-    if (r->n_dyn > 0 && r->n_envs == 0) return fail(r, SAS_ESTATE, "sas_render: scene has links but sas_set_link_poses has not been called");
-    SAS_CUDA(r, cudaSetDevice(r->device));
-    cudaStream_t st = (cudaStream_t)stream;
+// Enqueues the device work of one render on st (no host synchronisation, no allocation): the part that is
+// captured into a CUDA graph.
+static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb, float *d_depth, float *d_alpha, uint8_t *d_u8, int *d_nc,
+                          cudaStream_t st, int *n_launches) {
     const int I = r->I, C = r->C, W = r->W, H = r->H, tw = r->tile_w, th = r->tile_h, T = tw * th;
-    const size_t RT = (size_t)(C + I) * T, IT = (size_t)I * T, P = (size_t)I * W * H;
-    int launches = 0;
-
-    float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
-    uint8_t *d_u8 = out->rgb_u8;
-    int *d_nc = out->n_contrib;
-    const bool host_out = out->mem == SAS_MEM_HOST;
+    const size_t RT = (size_t)(C + I) * T, IT = (size_t)I * T;
     const bool ns = out->nerfstudio_post != 0;
-    int rc;
-    if (host_out) {
-        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
-        if (out->depth) { if ((rc = ensure(r, r->o_depth, P * 4))) return rc; d_depth = (float *)r->o_depth.p; }
-        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
-        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8, P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8.p; }
-        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc, P * 4))) return rc; d_nc = (int *)r->o_nc.p; }
-    } else if (ns) {
-        if (!d_rgb) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
-        if (!d_alpha) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
-    }
-
+    int launches = 0;
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_count.p, 0, RT * 4, st));
     SAS_CUDA(r, cudaMemsetAsync(r->row_tile_cursor.p, 0, RT * 4, st));
     // group reach masks (sas_common.cuh): OR-ed by the link projection; all-ones = "composite every group"
@@ -502,6 +498,72 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     }
     SAS_STAGE(6);
 #undef SAS_STAGE
+    *n_launches = launches;
+    return SAS_OK;
+}
+
+int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
+    if (!r || !out) return SAS_EINVAL;
+    if (!r->cameras_set) return fail(r, SAS_ESTATE, "sas_render: sas_set_cameras has not been called");
+    if (r->n_dyn > 0 && r->n_envs == 0) return fail(r, SAS_ESTATE, "sas_render: scene has links but sas_set_link_poses has not been called");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t P = (size_t)r->I * r->W * r->H;
+
+    float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
+    uint8_t *d_u8 = out->rgb_u8;
+    int *d_nc = out->n_contrib;
+    const bool host_out = out->mem == SAS_MEM_HOST;
+    const bool ns = out->nerfstudio_post != 0;
+    int rc;
+    if (host_out) {
+        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
+        if (out->depth) { if ((rc = ensure(r, r->o_depth, P * 4))) return rc; d_depth = (float *)r->o_depth.p; }
+        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
+        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8, P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8.p; }
+        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc, P * 4))) return rc; d_nc = (int *)r->o_nc.p; }
+    } else if (ns) {
+        if (!d_rgb) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
+        if (!d_alpha) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
+    }
+    if ((rc = ensure(r, r->img_max, (size_t)r->I * 4))) return rc;
+
+    // The step is ~25 launches, all with arguments that do not change from step to step (link poses and
+    // cameras live in fixed device buffers), so it is captured once into a CUDA graph and replayed: one
+    // launch per step instead of 25 (SAS_GRAPH=0 disables).  Not possible on the legacy / per-thread default
+    // streams (capture is not allowed there) or with per-stage timing events.
+    if (r->graph_mode < 0) {
+        const char *e = getenv("SAS_GRAPH");
+        r->graph_mode = e ? atoi(e) : 1;
+    }
+    const bool can_graph = r->graph_mode != 0 && !r->stage_timing && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    int launches = 0;
+    if (can_graph) {
+        sas_renderer::GraphKey key;
+        memset(&key, 0, sizeof(key));  // padding bytes take part in the memcmp below
+        key.I = r->I; key.C = r->C; key.W = r->W; key.H = r->H; key.ns = ns ? 1 : 0; key.flags = sas_variant_flags();
+        for (int k = 0; k < 3; k++) key.bg[k] = out->background[k];
+        key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc;
+        key.max_isects = r->max_isects; key.buf_gen = r->buf_gen;
+        if (!r->graph_exec || memcmp(&key, &r->graph_key, sizeof(key)) != 0) {
+            if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            SAS_CUDA(r, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != SAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(r, SAS_ECUDA, std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&r->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { r->graph_exec = nullptr; return fail(r, SAS_ECUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce)); }
+            memcpy(&r->graph_key, &key, sizeof(key));
+            r->graph_launches = launches;
+        }
+        SAS_CUDA(r, cudaGraphLaunch(r->graph_exec, st));
+        launches = r->graph_launches;
+    } else {
+        if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
+    }
     r->last_launches = launches;
     r->rendered = true;
     if (host_out) {

@@ -121,60 +121,92 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final(const unsigned *__res
     }
 }
 
-// Emission reserves bucket slots per CTA: Gaussians covering at most EMIT_FAST_TILES tiles take a
-// rank from a shared-memory counter per tile, the CTA then reserves each touched tile's range with
-// ONE global atomic, and the pairs are written at base + rank.  (One global atomic-with-return per
-// intersection was latency bound: 3.7 % issue utilisation, 310 warps stalled per issue.)  Gaussians
-// covering more tiles, and images with more tiles than fit in shared memory, use a global atomic
-// per intersection.  Slot order inside a bucket is arbitrary; the bucket sort fixes it.
-constexpr int EMIT_FAST_TILES = 4;
+// Emission.  A CTA takes 256 Gaussians of one row.  If one of them covers more than EMIT_FLAT_MIN_TILES
+// tiles, the CTA treats its (Gaussian, tile) intersections as ONE flattened list (block scan of the
+// per-Gaussian tile counts, then a binary search per list entry), so the threads share the work evenly
+// however skewed the footprints are -- a single screen-filling Gaussian (2 700 tiles at 720p) walked by
+// one thread used to hold its CTA for milliseconds; otherwise every thread walks its own few tiles.  Slots are reserved per
+// CTA in three shared-memory phases:
+//   1. every intersection counts into s_cnt[tile];
+//   2. one thread per touched tile reserves the CTA's range of that bucket with ONE global atomic
+//      (s_base) and clears the counter (a scan over all tiles: a touched-tile list appended through one
+//      shared counter serialised ~2000 same-address shared atomics per CTA at 1080p);
+//   3. every intersection takes a fresh rank from s_cnt[tile] again and writes its pair at
+//      s_base + rank.  The ranks of phase 1 and 3 differ, but any assignment of the reserved slots is
+//      fine: slot order inside a bucket is arbitrary, the bucket sort fixes it.
+// (One global atomic-with-return per intersection is latency bound: 3.7 % issue utilisation on the
+// pusht batch.)  Images with more tiles than fit in shared memory (> SAS_SMEM_TILES_MAX) skip phases
+// 1-2 and take a global atomic per intersection, still from the flattened list.
+constexpr unsigned EMIT_FLAT_MIN_TILES = 16;
 
 __global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bins, SasRowSpan span, int tile_w, int tile_h,
                                                    const int *__restrict__ row_tile_offset, unsigned int *__restrict__ row_tile_cursor,
                                                    uint2 *__restrict__ pairs, long long capacity, int smem_tiles) {
-    extern __shared__ unsigned int s_emit[];  // [smem_tiles] counts, then [smem_tiles] bases
+    extern __shared__ unsigned int s_emit[];  // [smem_tiles] counts, [smem_tiles] bases
     unsigned int *s_cnt = s_emit, *s_base = s_emit + smem_tiles;
+    __shared__ uint2 s_bn[256];
+    __shared__ unsigned int s_pre[257];
+    __shared__ unsigned int s_wsum[8];
     for (int t = threadIdx.x; t < smem_tiles; t += 256) s_cnt[t] = 0u;
-    if (smem_tiles) __syncthreads();
 
     const int local = blockIdx.x * 256 + threadIdx.x;
     const int row = blockIdx.y;
     uint2 bn = make_uint2(0u, 0u);
     if (local < span.n) bn = __ldg(bins + (size_t)span.rec0 + (size_t)row * span.n + local);
-    const bool vis = bn.x != 0u;  // a visible Gaussian always has x1 >= 1
+    s_bn[threadIdx.x] = bn;
+    // bn.x == 0 (culled) gives a 0 x 0 rectangle: a visible Gaussian always has x1 >= 1
     const int x0 = bn.x & 0xff, y0 = (bn.x >> 8) & 0xff, x1 = (bn.x >> 16) & 0xff, y1 = bn.x >> 24;
+    const unsigned ntile = (unsigned)((x1 - x0) * (y1 - y0));
+    // CTA-uniform choice (also the barrier that publishes s_cnt / s_bn): flattened list only if some Gaussian
+    // of the CTA covers many tiles; otherwise every thread walks its own small rectangle (no searches)
+    const bool flat = __syncthreads_or(ntile > EMIT_FLAT_MIN_TILES);
+    unsigned total = 0;
+    if (flat) {
+        const unsigned pre = block_exclusive_scan(ntile, &total, s_wsum);
+        s_pre[threadIdx.x] = pre;
+        if (threadIdx.x == 0) s_pre[256] = total;
+        __syncthreads();
+    }
     const size_t tbase = (size_t)(span.row0 + row) * tile_w * tile_h;
-    const unsigned gid = (unsigned)(span.g0 + local);  // canonical Gaussian index
-    const bool fast = vis && smem_tiles && (x1 - x0) * (y1 - y0) <= EMIT_FAST_TILES;
-    const int rw = x1 - x0, ntile = rw * (y1 - y0);
-    unsigned rank[EMIT_FAST_TILES];
-    if (fast) {
-#pragma unroll
-        for (int q = 0; q < EMIT_FAST_TILES; q++)  // fixed trip count keeps rank[] in registers
-            if (q < ntile) rank[q] = atomicAdd(&s_cnt[(y0 + q / rw) * tile_w + x0 + q % rw], 1u);
-    } else if (vis) {
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const size_t t = tbase + (size_t)y * tile_w + x;
-                const long long pos = (long long)__ldg(row_tile_offset + t) + (long long)atomicAdd(row_tile_cursor + t, 1u);
-                if (pos < capacity) pairs[pos] = make_uint2(bn.y, gid);
+    const unsigned gid0 = (unsigned)(span.g0 + blockIdx.x * 256);  // canonical index of the CTA's first Gaussian
+
+    // f(g, t) for every intersection this thread is responsible for: Gaussian g of the CTA, tile t of the image
+    auto for_each_entry = [&](auto f) {
+        if (flat) {
+            for (unsigned k = threadIdx.x; k < total; k += 256) {
+                int lo = 0, hi = 256;  // largest g with s_pre[g] <= k
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_pre[mid] <= k) lo = mid; else hi = mid;
+                }
+                const unsigned bx = s_bn[lo].x, r = k - s_pre[lo];
+                const int gx0 = bx & 0xff, gy0 = (bx >> 8) & 0xff, rw = (int)((bx >> 16) & 0xff) - gx0;
+                const int dy = (int)r / rw;
+                f(lo, (gy0 + dy) * tile_w + gx0 + ((int)r - dy * rw));
             }
-    }
-    if (!smem_tiles) return;
-    __syncthreads();
-    for (int t = threadIdx.x; t < smem_tiles; t += 256) {
-        const unsigned c = s_cnt[t];
-        if (c) s_base[t] = (unsigned)__ldg(row_tile_offset + tbase + t) + atomicAdd(row_tile_cursor + tbase + t, c);
-    }
-    __syncthreads();
-    if (fast) {
-#pragma unroll
-        for (int q = 0; q < EMIT_FAST_TILES; q++)
-            if (q < ntile) {
-                const long long pos = (long long)s_base[(y0 + q / rw) * tile_w + x0 + q % rw] + (long long)rank[q];
-                if (pos < capacity) pairs[pos] = make_uint2(bn.y, gid);
+        } else {
+            for (int y = y0; y < y1; y++)
+                for (int x = x0; x < x1; x++) f((int)threadIdx.x, y * tile_w + x);
+        }
+    };
+
+    if (smem_tiles) {
+        for_each_entry([&](int, int t) { atomicAdd(&s_cnt[t], 1u); });
+        __syncthreads();
+        for (int t = threadIdx.x; t < smem_tiles; t += 256) {
+            const unsigned c = s_cnt[t];
+            if (c) {
+                s_base[t] = (unsigned)__ldg(row_tile_offset + tbase + t) + atomicAdd(row_tile_cursor + tbase + t, c);
+                s_cnt[t] = 0u;
             }
+        }
+        __syncthreads();
     }
+    for_each_entry([&](int g, int t) {
+        const long long pos = smem_tiles ? (long long)s_base[t] + (long long)atomicAdd(&s_cnt[t], 1u)
+                                         : (long long)__ldg(row_tile_offset + tbase + t) + (long long)atomicAdd(row_tile_cursor + tbase + t, 1u);
+        if (pos < capacity) pairs[pos] = make_uint2(s_bn[g].y, gid0 + (unsigned)g);
+    });
 }
 
 // K5: merged[image,tile] = stable merge of the view's sorted background bucket and the image's

@@ -355,7 +355,8 @@ int g_comp_sms = 148;
 
 cudaError_t sas_composite_init(int n_sms) {
     g_comp_sms = n_sms > 0 ? n_sms : 148;
-    return cudaSuccess;
+    const int vf = sas_variant_flags();
+    return cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
 }
 
 // Registers are capped at 32 so that 64 warps stay resident per SM (measured 4.5 % faster than 48).
@@ -369,12 +370,6 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
 #define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
     const int vf = sas_variant_flags();
-    static bool flags_uploaded = false;
-    if (!flags_uploaded) {
-        cudaError_t e = cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
-        if (e != cudaSuccess) return e;
-        flags_uploaded = true;
-    }
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
 #define SAS_COMP(W, M) composite_kernel<W, M><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
     const int mode = (vf & 1) ? ((vf & 64) ? 2 : 1) : 0;

@@ -213,13 +213,12 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
     return true;
 }
 
-constexpr int PROJ_FAST_TILES = 4;  // Gaussians covering at most this many tiles count through shared memory
 
 // One thread per (row, Gaussian) of a span: the background span runs once per VIEW (rows = distinct
 // cameras), the link span once per IMAGE (rows = env x camera) -- see sas_common.cuh.  Per-(row,tile)
 // counts are accumulated in shared memory per CTA (one global RED per touched tile per CTA instead
-// of one per intersection); Gaussians covering many tiles, and images with more tiles than fit in
-// shared memory, add to the global counters directly.
+// of one per intersection); images with more tiles than fit in shared memory add to the global
+// counters directly.
 template <int DEG, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
@@ -245,24 +244,69 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
     unsigned int *tc = row_tile_count + (size_t)(span.row0 + row) * T;
     // link span only (rows = images): per-(image,tile) mask of the 4x2 groups a link Gaussian can reach
     unsigned int *dm = tile_dyn_mask ? tile_dyn_mask + (size_t)row * T : nullptr;
-    if (vis) {
-        const int ntile = (x1 - x0) * (y1 - y0);
-        const bool fast = smem_tiles && ntile <= PROJ_FAST_TILES;
-        const SasGroupReach gr = sas_group_reach(reach);
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const int t = y * tile_w + x;
-                if (fast) atomicAdd(s_cnt + t, 1u); else atomicAdd(tc + t, 1u);
-                if (dm) {
-                    const unsigned m = sas_group_reach_mask(gr, x, y);
-                    // read first: after the first few Gaussians of a CTA the bits are already set
-                    if (smem_masks) {
-                        if ((s_mask[t] & m) != m) atomicOr(s_mask + t, m);
-                    } else if ((__ldcg(dm + t) & m) != m) {
-                        atomicOr(dm + t, m);
-                    }
-                }
+    // If a Gaussian of the CTA covers many tiles, the CTA's (Gaussian, tile) intersections are counted as one
+    // flattened list (block scan of the tile counts + a binary search per entry, as in emit_kernel), so a
+    // screen-filling Gaussian does not leave 255 threads waiting for the one that owns it; otherwise every
+    // thread counts its own few tiles.
+    __shared__ unsigned int s_pre[257];
+    __shared__ unsigned int s_rect[256];
+    __shared__ unsigned int s_wsum[8];
+    __shared__ SasGroupReach s_gr[256];
+    const unsigned ntile = vis ? (unsigned)((x1 - x0) * (y1 - y0)) : 0u;
+    const SasGroupReach my_gr = sas_group_reach(reach);
+    auto count_one = [&](const SasGroupReach &gr, int x, int y) {
+        const int t = y * tile_w + x;
+        if (smem_tiles) atomicAdd(s_cnt + t, 1u); else atomicAdd(tc + t, 1u);
+        if (dm) {
+            const unsigned m = sas_group_reach_mask(gr, x, y);
+            // read first: after the first few Gaussians of a CTA the bits are already set
+            if (smem_masks) {
+                if ((s_mask[t] & m) != m) atomicOr(s_mask + t, m);
+            } else if ((__ldcg(dm + t) & m) != m) {
+                atomicOr(dm + t, m);
             }
+        }
+    };
+    if (__syncthreads_or(ntile > 16u)) {
+        s_rect[threadIdx.x] = vis ? ((unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24)) : 0u;
+        if (dm) s_gr[threadIdx.x] = my_gr;
+        unsigned total;
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            unsigned inc = ntile;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            unsigned pre = 0;
+            total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const unsigned sw = s_wsum[w];
+                if (w < warp) pre += sw;
+                total += sw;
+            }
+            s_pre[threadIdx.x] = pre + inc - ntile;
+            if (threadIdx.x == 0) s_pre[256] = total;
+            __syncthreads();
+        }
+        for (unsigned k = threadIdx.x; k < total; k += 256) {
+            int lo = 0, hi = 256;  // largest g with s_pre[g] <= k
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_pre[mid] <= k) lo = mid; else hi = mid;
+            }
+            const unsigned bx = s_rect[lo], r = k - s_pre[lo];
+            const int gx0 = bx & 0xff, gy0 = (bx >> 8) & 0xff, rw = (int)((bx >> 16) & 0xff) - gx0;
+            const int dy = (int)r / rw;
+            count_one(s_gr[lo], gx0 + ((int)r - dy * rw), gy0 + dy);
+        }
+    } else if (vis) {
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) count_one(my_gr, x, y);
     }
     {  // one counter update per warp instead of one per thread
         const unsigned m = __ballot_sync(0xffffffffu, vis);

@@ -48,6 +48,10 @@ class SplatRenderer:
         self._h = h
         self.max_images, self.max_envs = int(max_images), int(max_envs)
         self.I = self.W = self.H = 0
+        # libsas replays a CUDA graph of the step when it is given a real (non-default) stream; when the caller
+        # works on torch's default stream the renderer therefore runs on a side stream of its own, ordered
+        # against the caller's stream with event waits on both sides.
+        self._own_stream = torch.cuda.Stream(device=self.device)
         self._pinned: Dict[str, "torch.Tensor"] = {}
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -63,9 +67,22 @@ class SplatRenderer:
             pass
 
     def _stream(self, stream=None) -> C.c_void_p:
+        """cudaStream_t for a call.  Explicit stream: used as is.  Otherwise torch's current stream -- unless that is
+        the legacy default stream (no graph capture there): then the renderer's own stream, after the caller's work."""
         if stream is None:
             stream = self._torch.cuda.current_stream(self.device)
+            if int(stream.cuda_stream) == 0:
+                self._own_stream.wait_stream(stream)
+                self._handoff = stream
+                stream = self._own_stream
         return C.c_void_p(int(stream.cuda_stream))
+
+    def _handback(self) -> None:
+        """Make the caller's stream wait for what was enqueued on the renderer's own stream."""
+        h = getattr(self, "_handoff", None)
+        if h is not None:
+            h.wait_stream(self._own_stream)
+            self._handoff = None
 
     # -- per-step inputs --------------------------------------------------------------------
     def set_link_poses(self, poses, stream=None) -> None:
@@ -82,6 +99,7 @@ class SplatRenderer:
             p = _f32c(poses.cpu().numpy() if isinstance(poses, torch.Tensor) else poses).reshape(-1, self.L, 12)
             code = self._lib.sas_set_link_poses(self._h, p.ctypes.data, p.shape[0], L.SAS_MEM_HOST, self._stream(stream))
         L.check(self._lib, self._h, code)
+        self._handback()
 
     def set_pose_model(self, scale: float, Ri, ti, weld_t, fk_R, fk_t) -> None:
         """Constants of the reference's link-pose algebra (splat_handler.py:62-83, :158-163, :229-235): after this,
@@ -109,6 +127,7 @@ class SplatRenderer:
             b = np.ascontiguousarray(body_wxyz_xyz, dtype=np.float64).reshape(-1, self.L, 7)
             code = self._lib.sas_set_link_poses_from_bodies(self._h, b.ctypes.data, b.shape[0], L.SAS_MEM_HOST, self._stream(stream))
         L.check(self._lib, self._h, code)
+        self._handback()
 
     def unproject_depth(self, depth, K, max_depth: float = 1e10, stream=None):
         """Pinhole unprojection of nerfstudio_utils.py:441-452 on the device: depth [I,H,W] (CUDA float32 tensor) ->
@@ -124,6 +143,7 @@ class SplatRenderer:
         L.check(self._lib, self._h, self._lib.sas_unproject_depth(self._h, C.c_void_p(d.data_ptr()), I, W, H, Kf.ctypes.data, float(max_depth),
                                                                   C.c_void_p(xyz.data_ptr()), C.c_void_p(valid.data_ptr()), L.SAS_MEM_DEVICE,
                                                                   self._stream(stream)))
+        self._handback()
         return xyz, valid.bool()
 
     def set_cameras(self, viewmats, Ks, width: int, height: int, env_of_image: Optional[Sequence[int]] = None, stream=None) -> None:
@@ -140,6 +160,7 @@ class SplatRenderer:
         code = self._lib.sas_set_cameras(self._h, vm.ctypes.data, K.ctypes.data, env.ctypes.data if env is not None else None,
                                          I, int(width), int(height), self._stream(stream))
         L.check(self._lib, self._h, code)
+        self._handback()
         self.I, self.W, self.H = I, int(width), int(height)
 
     # -- render -----------------------------------------------------------------------------
@@ -186,6 +207,7 @@ class SplatRenderer:
                 L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
                 if self.stats()["overflow"]:
                     raise L.SasError(-4, "intersection buffers overflowed twice")
+        self._handback()
         return {n: bufs[n] for n in names}
 
     def reserve_isects(self, n: int) -> None:

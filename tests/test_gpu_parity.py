@@ -177,6 +177,46 @@ def test_rendering_is_deterministic_and_host_path_matches():
     r.close()
 
 
+def test_cuda_graph_replay_equals_direct_launches():
+    """sas_render replays a CUDA graph of the step on real streams; per-stage timing (events between the stages)
+    and the legacy default stream take the direct-launch path.  All must agree bit for bit, also after the
+    inputs, the outputs or the image count change (graph invalidation)."""
+    sc = S.make_synthetic_scene(15000, 2, seed=29, link_counts=(800, 400))
+    W, H = 144, 112
+    vms = S.ring_cameras(4, (0, 0, 0), seed=8)
+    r = SplatRenderer(sc, max_images=4, max_envs=3, max_width=W, max_height=H)
+    names = ("rgb", "depth", "alpha", "n_contrib")
+    r.set_cameras(vms, S.fov_intrinsics(W, H), W, H, [0, 1, 2, 1])
+    poses_a, poses_b = S.random_link_poses(3, 2, seed=1), S.random_link_poses(3, 2, seed=2)
+    got = {}
+    for tag, poses in (("a", poses_a), ("b", poses_b), ("a2", poses_a)):
+        r.set_link_poses(poses)
+        got[tag] = {k: v.clone() for k, v in r.render(names).items()}      # own stream -> graph (captured once, replayed)
+    for k in names:
+        assert torch.equal(got["a"][k], got["a2"][k]), k
+        assert not torch.equal(got["a"]["rgb"], got["b"]["rgb"])
+    r.set_stage_timing(True)                                                 # direct launches
+    r.set_link_poses(poses_b)
+    direct = r.render(names)
+    assert set(r.stage_ms()) == set(r.STAGES)
+    r.set_stage_timing(False)
+    for k in names:
+        assert torch.equal(direct[k], got["b"][k]), k
+    s2 = torch.cuda.Stream()
+    with torch.cuda.stream(s2):                                              # caller's own stream -> graph on that stream
+        r.set_link_poses(torch.from_numpy(poses_b).cuda())
+        on_s2 = r.render(names)
+    s2.synchronize()
+    for k in names:
+        assert torch.equal(on_s2[k], got["b"][k]), k
+    r.set_cameras(vms[:2], S.fov_intrinsics(W, H), W, H, [0, 1])             # fewer images: the graph is rebuilt
+    r.set_link_poses(poses_a)
+    two = r.render(names)
+    for k in names:
+        assert torch.equal(two[k], got["a"][k][:2]), k
+    r.close()
+
+
 def test_overflow_is_reported_and_regrown():
     sc = S.make_synthetic_scene(30000, 1, seed=17)
     W, H = 128, 128
