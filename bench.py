@@ -238,7 +238,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": E_PER_GPU, "images_per_gpu": I, "width": W, "height": H,
                        "n_gaussians": sc.N, "sh_degree": SH_DEG, "n_links": sc.L, "parallelism": f"env-shard x{world}, scene replicated",
-                       "l2": "per-step working set (records+bins+pairs ~1 GB) exceeds the 126 MB L2 and 4 pose batches rotate; no explicit flush"},
+                       "l2": "per-step working set (records + bins + pairs + merged ids + images ~0.3 GB) exceeds the 126 MB L2 and 4 pose batches rotate; no explicit flush"},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pose_sets[0].nbytes), "d2h_bytes_per_step": int(I * H * W * (3 + 4)),
                     "outputs": "uint8 RGB [I,H,W,3] + f32 depth [I,H,W] into pinned host memory via sas_render(mem=HOST)"},
@@ -273,8 +273,7 @@ def cpu_baseline(sc, cam, K, poses, envs: int, reps: int, threads: int = 0) -> d
     nerfstudio) is not installable here."""
     import oracle
 
-    if threads:
-        oracle.set_num_threads(threads)
+    oracle.set_num_threads(threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     d = sc.as_oracle_dict()
     vms = np.repeat(cam, envs, axis=0)
     Ks = np.repeat(K[None], envs, axis=0)
@@ -296,6 +295,8 @@ def run_reference(args):
     sc, cam, K, pose_sets = build_workload(0)
     import oracle
 
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread it can
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     envs = 32
     d = sc.as_oracle_dict()
     vms, Ks = np.repeat(cam, envs, axis=0), np.repeat(K[None], envs, axis=0)

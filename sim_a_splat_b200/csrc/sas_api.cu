@@ -66,6 +66,8 @@ struct sas_renderer {
     };
     cudaGraphExec_t graph_exec = nullptr;
     GraphKey graph_key{};
+    GraphKey pending_key{};          // a graph is only built for a key seen twice in a row
+    bool pending_valid = false;
     int graph_launches = 0;
     unsigned long long buf_gen = 0;  // bumped whenever a work buffer is (re)allocated: invalidates the graph
     int graph_mode = -1;             // SAS_GRAPH environment variable (default on)
@@ -545,22 +547,34 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         for (int k = 0; k < 3; k++) key.bg[k] = out->background[k];
         key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc;
         key.max_isects = r->max_isects; key.buf_gen = r->buf_gen;
-        if (!r->graph_exec || memcmp(&key, &r->graph_key, sizeof(key)) != 0) {
-            if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
-            cudaGraph_t graph = nullptr;
-            SAS_CUDA(r, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches);
-            cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            if (rc != SAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) return fail(r, SAS_ECUDA, std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&r->graph_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) { r->graph_exec = nullptr; return fail(r, SAS_ECUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce)); }
-            memcpy(&r->graph_key, &key, sizeof(key));
-            r->graph_launches = launches;
+        const bool have = r->graph_exec && memcmp(&key, &r->graph_key, sizeof(key)) == 0;
+        if (!have && !(r->pending_valid && memcmp(&key, &r->pending_key, sizeof(key)) == 0)) {
+            // first sight of this key (e.g. freshly allocated output tensors every call): launch directly and
+            // remember it; capturing + instantiating costs more than one step saves
+            memcpy(&r->pending_key, &key, sizeof(key));
+            r->pending_valid = true;
+            if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
+        } else {
+            if (!have) {
+                if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                SAS_CUDA(r, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+                rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches);
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc != SAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(r, SAS_ECUDA, std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&r->graph_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) {
+                    r->graph_exec = nullptr;
+                    return fail(r, SAS_ECUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+                }
+                memcpy(&r->graph_key, &key, sizeof(key));
+                r->graph_launches = launches;
+            }
+            SAS_CUDA(r, cudaGraphLaunch(r->graph_exec, st));
+            launches = r->graph_launches;
         }
-        SAS_CUDA(r, cudaGraphLaunch(r->graph_exec, st));
-        launches = r->graph_launches;
     } else {
         if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
     }
