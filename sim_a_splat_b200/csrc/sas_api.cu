@@ -147,7 +147,7 @@ int sas_variant_flags() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SAS_VARIANT");
-        v = e ? (int)strtol(e, nullptr, 0) & 0xff : 0xcf;
+        v = e ? (int)strtol(e, nullptr, 0) & 0x1ff : 0xcf;
     }
     return v;
 }
@@ -468,11 +468,18 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
         launches += 1;
     }
     SAS_STAGE(1);
-    SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st, &launches));
-    SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
-                                &launches));
-    SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, work, (unsigned char *)r->view_needed.p,
-                                      (int *)r->sort_list.p, (int *)r->comp_list.p, st, &launches));
+    if (sas_scan_lists_fused_ok(C, I, T)) {
+        SAS_CUDA(r, sas_launch_scan_lists_fused(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, roff, ioff, r->counters, r->max_isects,
+                                                work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p, (int *)r->comp_list.p, st,
+                                                &launches));
+    } else {
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
+                                    &launches));
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
+                                    &launches));
+        SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, work, (unsigned char *)r->view_needed.p,
+                                          (int *)r->sort_list.p, (int *)r->comp_list.p, st, &launches));
+    }
     SAS_STAGE(2);
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;

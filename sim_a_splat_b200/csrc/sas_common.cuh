@@ -165,6 +165,7 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //   bit 6  compositor: each staged record's 32-bit group reach mask is computed once per CTA (by the thread
 //          that staged it) instead of every warp testing every record against its own four groups
 //   bit 7  compositor: warp -> footprint map rotated with the work-item index (evens out the four schedulers)
+//   bit 8  scans + work lists as eleven small kernels even when the single-CTA fused kernel applies
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -195,6 +196,12 @@ cudaError_t sas_launch_unproject(const float *depth, int I, int W, int H, float 
 cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C, int I,
                                   int W, int H, int tile_w, int tile_h, SasWork *work, unsigned char *view_tile_needed, int *sort_list,
                                   int *comp_list, cudaStream_t st, int *n_launches);
+// one-launch replacement of the two sas_launch_scan calls + sas_launch_work_lists for small problems
+bool sas_scan_lists_fused_ok(int C, int I, int T);
+cudaError_t sas_launch_scan_lists_fused(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C,
+                                        int I, int W, int H, int tile_w, int tile_h, int *row_tile_offset, int *img_tile_offset,
+                                        SasCounters *counters, long long capacity, SasWork *work, unsigned char *view_tile_needed,
+                                        int *sort_list, int *comp_list, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
