@@ -129,15 +129,16 @@ typedef struct {
     double scale;             /* s  */
     double Ri[9];             /* row-major */
     double ti[3];
-    double weld_t[3];
-    const double *fk_R;       /* [L,9] row-major */
+    const double *fk_R;       /* [L,9] row-major; identity for a free body registered at the origin (the T-block) */
     const double *fk_t;       /* [L,3] */
+    const double *body_offset;/* [L,3] added to the body position: the weld translation for robot bodies (:250-257),
+                                 zero for free bodies (:296-310); NULL = all zero */
 } sas_pose_model;
 int sas_set_pose_model(sas_renderer *r, const sas_pose_model *model);
 
 /* body poses [n_envs, L, 7] fp64 = (quaternion wxyz as sent -- normalised here, :239-240 -- | position xyz), the
  * fields of lcmt_viewer_draw for the robot's bodies (manipulator_env.py:377-390).  Computes
- * rot = Ri Rm Rfk^T Ri^T, pos = -rot ti - s Ri Rm Rfk^T tfk + s Ri (p + weld_t) + ti in fp64 and stores the
+ * rot = Ri Rm Rfk^T Ri^T, pos = -rot ti - s Ri Rm Rfk^T tfk + s Ri (p + body_offset) + ti in fp64 and stores the
  * fp32 [n_envs, L, 12] block sas_set_link_poses would have been given. */
 int sas_set_link_poses_from_bodies(sas_renderer *r, const double *body_wxyz_xyz, int n_envs, int mem, void *stream);
 

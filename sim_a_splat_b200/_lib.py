@@ -55,7 +55,7 @@ class Stats(C.Structure):
 
 class PoseModel(C.Structure):
     _fields_ = [("n_links", C.c_int32), ("scale", C.c_double), ("Ri", C.c_double * 9), ("ti", C.c_double * 3),
-                ("weld_t", C.c_double * 3), ("fk_R", C.c_void_p), ("fk_t", C.c_void_p)]
+                ("fk_R", C.c_void_p), ("fk_t", C.c_void_p), ("body_offset", C.c_void_p)]
 
 
 class SasError(RuntimeError):

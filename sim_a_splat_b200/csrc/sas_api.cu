@@ -45,7 +45,7 @@ struct sas_renderer {
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
     DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask;
     SasPoseModel pose_model{};            // device pointers inside; pose_model.L == 0: not set
-    double *fk_dev = nullptr;             // [L,12]: fk_R then fk_t
+    double *fk_dev = nullptr;             // [L,15]: fk_R, fk_t, body_offset
     DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
     cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
@@ -299,16 +299,21 @@ int sas_set_pose_model(sas_renderer *r, const sas_pose_model *model) {
     if (model->n_links != r->L || r->L <= 0 || !model->fk_R || !model->fk_t)
         return fail(r, SAS_EINVAL, "sas_set_pose_model: n_links must equal the scene's link count (> 0) and fk_R / fk_t must be given");
     SAS_CUDA(r, cudaSetDevice(r->device));
-    if (!r->fk_dev) SAS_CUDA(r, cudaMalloc(&r->fk_dev, sizeof(double) * 12 * (size_t)r->L));
+    if (!r->fk_dev) SAS_CUDA(r, cudaMalloc(&r->fk_dev, sizeof(double) * 15 * (size_t)r->L));
     SAS_CUDA(r, cudaMemcpy(r->fk_dev, model->fk_R, sizeof(double) * 9 * (size_t)r->L, cudaMemcpyHostToDevice));
     SAS_CUDA(r, cudaMemcpy(r->fk_dev + 9 * (size_t)r->L, model->fk_t, sizeof(double) * 3 * (size_t)r->L, cudaMemcpyHostToDevice));
+    if (model->body_offset)
+        SAS_CUDA(r, cudaMemcpy(r->fk_dev + 12 * (size_t)r->L, model->body_offset, sizeof(double) * 3 * (size_t)r->L, cudaMemcpyHostToDevice));
+    else
+        SAS_CUDA(r, cudaMemset(r->fk_dev + 12 * (size_t)r->L, 0, sizeof(double) * 3 * (size_t)r->L));
     SasPoseModel &m = r->pose_model;
     m.L = r->L;
     m.s = model->scale;
     for (int i = 0; i < 9; i++) m.Ri[i] = model->Ri[i];
-    for (int i = 0; i < 3; i++) { m.ti[i] = model->ti[i]; m.weld_t[i] = model->weld_t[i]; }
+    for (int i = 0; i < 3; i++) m.ti[i] = model->ti[i];
     m.fk_R = r->fk_dev;
     m.fk_t = r->fk_dev + 9 * (size_t)r->L;
+    m.offset = r->fk_dev + 12 * (size_t)r->L;
     return SAS_OK;
 }
 

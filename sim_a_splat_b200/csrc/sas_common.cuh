@@ -182,11 +182,11 @@ struct SasViewBuf {
     int *n_contrib;  // [C,H,W]
 };
 
-// Constants of the link-pose algebra (sas_pose.cu); fk_R / fk_t are device pointers [L,9] / [L,3].
+// Constants of the link-pose algebra (sas_pose.cu); fk_R / fk_t / offset are device pointers [L,9] / [L,3] / [L,3].
 struct SasPoseModel {
     int L;
-    double s, Ri[9], ti[3], weld_t[3];
-    const double *fk_R, *fk_t;
+    double s, Ri[9], ti[3];
+    const double *fk_R, *fk_t, *offset;
 };
 
 // Launchers (each returns the cudaError_t of the launch).

@@ -3,7 +3,7 @@
 // (1) link_pose_kernel: the pose algebra of SplatHandler.draw_handler
 //     (/root/reference/sim_a_splat/splat/splat_handler.py:250-281), batched over (env, link) on the
 //     device instead of ~10 small NumPy products per link per env in Python:
-//         Rm  = R(q / |q|),  tm = p + weld_t
+//         Rm  = R(q / |q|),  tm = p + body_offset  (the weld translation for robot bodies, 0 for free bodies)
 //         rot = Ri Rm Rfk^T Ri^T
 //         pos = -rot ti - s Ri Rm Rfk^T tfk + s Ri tm + ti
 //     evaluated in fp64 (the reference's precision; B200 keeps full-rate-enough FP64 for 8 x 256
@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(128) link_pose_kernel(const double *__restrict
     const double Rm[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z),     2 * (x * z + w * y),
                           2 * (x * y + w * z),     1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
                           2 * (x * z - w * y),     2 * (y * z + w * x),     1 - 2 * (x * x + y * y)};
-    const double tm[3] = {b[4] + m.weld_t[0], b[5] + m.weld_t[1], b[6] + m.weld_t[2]};
-    const double *Rfk = m.fk_R + 9 * l, *tfk = m.fk_t + 3 * l;
+    const double *Rfk = m.fk_R + 9 * l, *tfk = m.fk_t + 3 * l, *off = m.offset + 3 * l;
+    const double tm[3] = {b[4] + off[0], b[5] + off[1], b[6] + off[2]};
     double M1[9], A[9], rot[9];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) M1[3 * i + j] = m.Ri[3 * i] * Rm[j] + m.Ri[3 * i + 1] * Rm[3 + j] + m.Ri[3 * i + 2] * Rm[6 + j];  // Ri Rm

@@ -101,17 +101,18 @@ class SplatRenderer:
         L.check(self._lib, self._h, code)
         self._handback()
 
-    def set_pose_model(self, scale: float, Ri, ti, weld_t, fk_R, fk_t) -> None:
+    def set_pose_model(self, scale: float, Ri, ti, fk_R, fk_t, body_offset=None) -> None:
         """Constants of the reference's link-pose algebra (splat_handler.py:62-83, :158-163, :229-235): after this,
-        set_link_poses_from_bodies() composes rot / pos on the device (csrc/sas_pose.cu)."""
+        set_link_poses_from_bodies() composes rot / pos on the device (csrc/sas_pose.cu).  body_offset [L,3] is
+        added to each body position (the weld translation for robot bodies, zero for free bodies)."""
         fkR = np.ascontiguousarray(fk_R, dtype=np.float64).reshape(self.L, 9)
         fkt = np.ascontiguousarray(fk_t, dtype=np.float64).reshape(self.L, 3)
+        off = np.zeros((self.L, 3)) if body_offset is None else np.ascontiguousarray(body_offset, dtype=np.float64).reshape(self.L, 3)
         m = L.PoseModel()
         m.n_links, m.scale = self.L, float(scale)
         m.Ri = (C.c_double * 9)(*np.asarray(Ri, dtype=np.float64).reshape(9))
         m.ti = (C.c_double * 3)(*np.asarray(ti, dtype=np.float64).reshape(3))
-        m.weld_t = (C.c_double * 3)(*np.asarray(weld_t, dtype=np.float64).reshape(3))
-        m.fk_R, m.fk_t = fkR.ctypes.data, fkt.ctypes.data
+        m.fk_R, m.fk_t, m.body_offset = fkR.ctypes.data, fkt.ctypes.data, off.ctypes.data
         L.check(self._lib, self._h, self._lib.sas_set_pose_model(self._h, C.byref(m)))
 
     def set_link_poses_from_bodies(self, body_wxyz_xyz, stream=None) -> None:

@@ -28,6 +28,35 @@ URDF = """<?xml version="1.0"?>
   <link name="gripper"><visual><geometry><mesh filename="package://toyarm/meshes/g.obj"/></geometry><origin rpy="0 0 0" xyz="0 0 0"/><material name="Blue"/></visual></link>
 </robot>
 """
+TBLOCK_OBJ = """# T-block, metres (two boxes: bar 0.2 x 0.05, stem 0.05 x 0.15, height 0.04)
+v -0.1 -0.025 0.0
+v 0.1 -0.025 0.0
+v 0.1 0.025 0.0
+v -0.1 0.025 0.0
+v -0.1 -0.025 0.04
+v 0.1 -0.025 0.04
+v 0.1 0.025 0.04
+v -0.1 0.025 0.04
+v -0.025 -0.175 0.0
+v 0.025 -0.175 0.0
+v 0.025 -0.025 0.0
+v -0.025 -0.025 0.0
+v -0.025 -0.175 0.04
+v 0.025 -0.175 0.04
+v 0.025 -0.025 0.04
+v -0.025 -0.025 0.04
+f 1//1 2//1 3//1 4//1
+f 5//1 6//1 7//1 8//1
+f 1//1 2//1 6//1 5//1
+f 2//1 3//1 7//1 6//1
+f 3//1 4//1 8//1 7//1
+f 4//1 1//1 5//1 8//1
+f 9//1 10//1 11//1 12//1
+f 13//1 14//1 15//1 16//1
+f 9//1 10//1 14//1 13//1
+f 10//1 11//1 15//1 14//1
+f 12//1 9//1 13//1 16//1
+"""
 N_LINKS = 3  # masks for link0..link2; the 4th body (gripper) has a mesh pose but no splat group, like the xarm push gripper
 
 
@@ -60,8 +89,11 @@ def make_assets(root: Path, assets: dict, n_gaussians: int = 6000, sh_degree: in
              pre + "scales": torch.from_numpy(np.log(scales)), pre + "opacities": torch.from_numpy(logit(opac.astype(np.float64)).astype(np.float32))[:, None],
              pre + "features_dc": torch.from_numpy(sh[:, 0]), pre + "features_rest": torch.from_numpy(sh[:, 1:])}
     torch.save({"pipeline": state, "step": 1}, cdir / "step-000000001.ckpt")
+    tdir = root / "tblock_paper"
+    tdir.mkdir(parents=True)
+    (tdir / "tblock_paper.obj").write_text(TBLOCK_OBJ)
     return dict(root=str(root), obj=obj, cfg=cfg, package_path=str(root / "robot_description"), package_name="toyarm/", urdf_name="toyarm.urdf",
-                masks=masks, joint_config=joint_config, n=n_gaussians)
+                masks=masks, joint_config=joint_config, n=n_gaussians, task_assets_path=str(tdir), task_assets_name="tblock_paper.obj")
 
 
 class FakeManipulatorEnv:

@@ -185,16 +185,64 @@ def test_body_pose_block_reproduces_link_poses_through_the_oracle(toy):
     assert B.shape == (N_LINKS, 7) and B.dtype == np.float64 and m["fk_R"].shape == (N_LINKS, 3, 3) and m["fk_t"].shape == (N_LINKS, 3)
     rows = []
     for l in range(N_LINKS):
-        rot, pos = po.link_transform(B[l, :4], B[l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+        rot, pos = po.link_transform(B[l, :4], B[l, 4:], m["body_offset"][l], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
         rows.append(po.poses_to_rot12(rot, pos))
     np.testing.assert_allclose(np.stack(rows), h.link_poses_from_msg(msg), atol=2e-7)
     # a message without robot bodies leaves every link at its capture-time pose = identity transform
     empty = type("M", (), dict(num_links=0, robot_num=[], quaternion=[], position=[], link_name=[]))()
     B0 = h.body_poses_from_msg(empty)
     for l in range(N_LINKS):
-        rot, pos = po.link_transform(B0[l, :4], B0[l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+        rot, pos = po.link_transform(B0[l, :4], B0[l, 4:], m["body_offset"][l], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
         np.testing.assert_allclose(rot, np.eye(3), atol=1e-12)
         np.testing.assert_allclose(pos, 0.0, atol=1e-12)
+
+
+def test_task_mesh_becomes_one_more_link_group(toy):
+    """the reference draws the T-block as a viser mesh moved by icp o (q_hat, s p)
+    (splat_handler.py:199-219, :296-310); here its surface Gaussians are link group L, moved by the same link
+    algebra (fk = identity, no weld) -- both must put every point in the same place."""
+    from sim_a_splat_b200.ellipsoids.mesh_utils import load_obj, mesh_to_gaussians
+
+    mesh = load_obj(f"{toy['task_assets_path']}/{toy['task_assets_name']}")
+    assert mesh.vertices.shape == (16, 3) and mesh.faces.shape == (22, 3)  # quads fan-triangulated
+    m, q, sc_, op, sh = mesh_to_gaussians(mesh, 500, seed=1)
+    assert m.shape == (500, 3) and np.allclose(np.linalg.norm(q, axis=1), 1, atol=1e-6) and sh.shape == (500, 1, 3)
+    assert m[:, 2].min() >= -1e-9 and m[:, 2].max() <= 0.04 + 1e-9 and abs(m[:, 0]).max() <= 0.1 + 1e-9
+    assert np.all(sc_[:, 2] < sc_[:, 0])  # flat discs
+
+    weld = RigidTransformLite(translation=(0.05, -0.02, 0.01))
+    h = SplatHandler(toy["root"], toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"],
+                     task_assets_path=toy["task_assets_path"], task_assets_name=toy["task_assets_name"], sim_robot_weld_frame_transform=weld,
+                     n_task_gaussians=800)
+    assert h.task_splat_handle is not None and h.n_link_groups == N_LINKS + 1
+    sc = h.server.build_scene()
+    assert sc.L == N_LINKS + 1 and int((sc.link_id == N_LINKS).sum()) == 800
+    env = FakeManipulatorEnv(toy, seed=6)
+    env.reset(seed=6)
+    env.block[:] = [0.27, -0.12, 0.0, 0.8]
+    msg = env._generate_draw_msg()
+    h.draw_handler(msg)
+    # mesh-node semantics of the reference vs the link group: same world position for every surface point
+    mu_s = sc.means[sc.link_id == N_LINKS].astype(np.float64)
+    x_mesh = (mu_s - h.ti) @ h.Ri / h.scale_factor                      # Ri^T (mu - ti) / s
+    Rt, pt = tf.SO3(h.task_mesh_frame_handle.wxyz).as_matrix(), h.task_mesh_frame_handle.position
+    want = (h.scale_factor * x_mesh) @ Rt.T + pt
+    Rl, pl = tf.SO3(h.task_splat_handle.wxyz).as_matrix(), h.task_splat_handle.position
+    np.testing.assert_allclose(mu_s @ Rl.T + pl, want, atol=2e-6)
+    # the [L,12] block and the device-side pose model carry the task link last, weld-free
+    P = h.link_poses_from_msg(msg)
+    assert P.shape == (N_LINKS + 1, 12)
+    np.testing.assert_allclose(P[N_LINKS, :9].reshape(3, 3), Rl, atol=1e-6)
+    np.testing.assert_allclose(P[N_LINKS, 9:], pl, atol=1e-6)
+    B, pm = h.body_poses_from_msg(msg), h.pose_model()
+    assert B.shape == (N_LINKS + 1, 7) and np.all(pm["body_offset"][N_LINKS] == 0) and np.allclose(pm["body_offset"][0], weld.translation())
+    rows = [po.poses_to_rot12(*po.link_transform(B[l, :4], B[l, 4:], pm["body_offset"][l], pm["scale"], pm["Ri"], pm["ti"], pm["fk_R"][l], pm["fk_t"][l]))
+            for l in range(N_LINKS + 1)]
+    np.testing.assert_allclose(np.stack(rows), P, atol=2e-7)
+    # opting out, or a server that only speaks the viser protocol, leaves the task as an (undrawn) mesh node
+    h2 = SplatHandler(toy["root"], toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"],
+                      task_assets_path=toy["task_assets_path"], task_assets_name=toy["task_assets_name"], task_as_splats=False)
+    assert h2.task_splat_handle is None and h2.n_link_groups == N_LINKS
 
 
 def test_handler_rejects_rotated_weld_and_attached_frame_quirk(toy):

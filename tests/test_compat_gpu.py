@@ -107,6 +107,45 @@ def test_vec_renderer_matches_single_env_wrappers(toy):
     env.close()
 
 
+def test_task_block_is_rendered_and_follows_its_pose(toy):
+    """the PushT T-block (a viser mesh in the reference, splat_handler.py:199-219) is drawn as a link
+    group of surface Gaussians: it shows up in the observation in its red mesh colour, follows the block pose, and
+    the batched path (device-side pose composition with the weld-free task link) gives the same images."""
+    H, W = 72, 96
+    kw = dict(task_assets_path=toy["task_assets_path"], task_assets_name=toy["task_assets_name"])
+    from sim_a_splat_b200 import transforms as tf
+
+    env = SplatEnvWrapper(FakeManipulatorEnv(toy, seed=3), toy["root"], toy["obj"], toy["cfg"], **kw)
+    h = env.splat_handler
+    # a camera 0.3 splat units above the block's work area, looking at it (block positions below are metric, URDF frame)
+    target = h.scale_factor * (h.Ri @ np.array([0.07, 0.05, 0.02])) + h.ti
+    eye = target + 0.3 * (h.Ri @ (np.array([0.25, -0.35, 0.9]) / np.linalg.norm([0.25, -0.35, 0.9])))
+    cams = {0: dict(camera_setup((H, W))[0])}
+    cams[0]["local_frame"] = tf.SE3.from_matrix(np.linalg.inv(S.lookat_viewmat(eye, target, up=h.Ri[:, 2]).astype(np.float64)))
+    env._configure_cameras(cams)
+    env.reset(seed=5)
+    assert env.splat_handler.n_link_groups == N_LINKS + 1
+    frames, msgs = [], []
+    for block in ([0.0, 0.0, 0.0, 0.0], [0.15, 0.1, 0.0, 1.0]):
+        env.unwrapped.block[:] = block
+        obs, *_ = env.step(np.zeros(3))
+        ref = _oracle_views(env, H, W)
+        want = np.moveaxis(_to_u8(ref["rgb"][0]), -1, 0)
+        assert np.sum(obs["camera_0"] != want) == 0
+        frames.append(obs["camera_0"].astype(np.int32))
+        msgs.append(env.draw_msg)
+    changed = np.abs(frames[0] - frames[1]).sum(0) > 30
+    assert changed.sum() > 40                                       # the block moved in the image
+    red = (frames[0][0] > 180) & (frames[0][1] < 150) & (frames[0][2] < 150)
+    assert red.sum() > 20                                           # and it is the reference's mesh colour (0.956, 0.396, 0.365)
+    vec = VecSplatRenderer(env.splat_handler, cams, n_envs=2, fov=env.ch.camera.fov, background=env.splat_handler.server.background_rgb)
+    out = vec.render(msgs)["camera_0"]
+    for e in range(2):
+        assert np.abs(out[e].astype(np.int32) - frames[e]).max() <= 1   # device fp64 composition vs host quaternion round trip
+    vec.close()
+    env.close()
+
+
 def test_device_pose_composition_matches_pose_oracle(toy, assets):
     """sas_set_link_poses_from_bodies (csrc/sas_pose.cu) == oracle/pose_oracle.py:link_transform (pinned to the
     reference's draw_handler by tests/golden/draw_handler.npz), over many envs, incl. un-normalised quaternions."""
@@ -128,7 +167,7 @@ def test_device_pose_composition_matches_pose_oracle(toy, assets):
     want = np.empty_like(got)
     for e in range(E):
         for l in range(N_LINKS):
-            rot, pos = po.link_transform(body[e, l, :4], body[e, l, 4:], m["weld_t"], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
+            rot, pos = po.link_transform(body[e, l, :4], body[e, l, 4:], m["body_offset"][l], m["scale"], m["Ri"], m["ti"], m["fk_R"][l], m["fk_t"][l])
             want[e, l] = po.poses_to_rot12(rot, pos)
     np.testing.assert_allclose(got, want, atol=3e-7, rtol=0)
     # device-resident input gives the same block
