@@ -274,6 +274,14 @@ def test_full_size_config2_properties(assets):
         assert torch.equal(a[k], b[k]), k           # idempotent / deterministic despite atomics
         assert torch.equal(a[k][5], a[k][200]), k   # same env state -> same image
     assert not torch.equal(a["rgb"][5], a["rgb"][6])
+    # host outputs: composited in 4 image ranges with the device->host copy of each overlapping the next
+    # (sas_render, pinned destinations); twice, so that the second call replays the captured graph
+    for _ in range(2):
+        h = r.render(names + ("rgb_u8",), to_host=True)
+        for k in names:
+            assert not h[k].is_cuda and torch.equal(h[k], a[k].cpu()), k
+    u8 = torch.floor(torch.clamp(a["rgb"], 0, 1) * 255.0 + 0.5).to(torch.uint8).cpu()
+    assert torch.equal(h["rgb_u8"], u8)
     pick = [0, 5, 77, 200, 255]
     ref = oracle.render(sc.as_oracle_dict(), np.repeat(cam, len(pick), axis=0), np.repeat(S.fov_intrinsics(W, H)[None], len(pick), 0),
                         W, H, poses[pick], np.arange(len(pick)), keep={"rgb", "depth", "alpha", "n_contrib"})
