@@ -126,6 +126,75 @@ class SimpleURDF:
         return [v for v in self.visuals if v.mesh_filename is not None]
 
 
+def _axis_angle_batch(axis: np.ndarray, q: np.ndarray) -> np.ndarray:
+    a = axis / (np.linalg.norm(axis) or 1.0)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    T = np.tile(np.eye(4), (q.shape[0], 1, 1))
+    T[:, :3, :3] = np.eye(3) + np.sin(q)[:, None, None] * K + (1 - np.cos(q))[:, None, None] * (K @ K)
+    return T
+
+
+class BatchedBodyPoseSource:
+    """Body poses for E envs at once from joint configurations -- the pose source of SURVEY.md 8f-1 for users
+    without Drake: the draw message of the reference (`ManipulatorSimEnv._generate_draw_msg`,
+    /root/reference/sim_a_splat/env/manipulator/manipulator_env.py:377-390) carries the world pose of every
+    robot body; here the same [E, B, 7] block (quaternion wxyz | position) comes from the URDF's forward
+    kinematics, vectorised over envs, for the bodies that carry visual meshes in URDF order -- the order in
+    which `SplatHandler` pairs bodies with link groups.  Feed it to `SplatRenderer.set_link_poses_from_bodies`
+    (with `SplatHandler.pose_model()`); a free body (the T-block) is appended by the caller."""
+
+    def __init__(self, urdf: "SimpleURDF", base: Optional[np.ndarray] = None):
+        self.urdf = urdf
+        self.base = np.eye(4) if base is None else np.asarray(base, dtype=np.float64)
+        self.joint_names = urdf.actuated_joint_names
+        self.bodies = [v.link for v in urdf.mesh_visuals()]
+        children = {j.child for j in urdf.joints}
+        self._roots = [l for l in urdf.links if l not in children]
+        order, known, pending = [], set(self._roots), list(urdf.joints)
+        while pending:  # parent-before-child joint order, resolved once
+            nxt = [j for j in pending if j.parent in known]
+            if not nxt:
+                raise ValueError("URDF joint graph is not a tree rooted at a link without parent")
+            for j in nxt:
+                order.append(j)
+                known.add(j.child)
+                pending.remove(j)
+        self._order = order
+
+    def link_fk(self, q: np.ndarray) -> Dict[str, np.ndarray]:
+        """q [E, n_actuated] -> {link: [E,4,4]} world transforms."""
+        q = np.asarray(q, dtype=np.float64).reshape(-1, len(self.joint_names))
+        E = q.shape[0]
+        col = {n: k for k, n in enumerate(self.joint_names)}
+        T = {l: np.tile(self.base, (E, 1, 1)) for l in self._roots}
+        for j in self._order:
+            if j.mimic is not None:
+                qj = q[:, col[j.mimic[0]]] * j.mimic[1] + j.mimic[2] if j.mimic[0] in col else np.zeros(E)
+            else:
+                qj = q[:, col[j.name]] if j.name in col else np.zeros(E)
+            if j.jtype in ("revolute", "continuous"):
+                M = _axis_angle_batch(j.axis, qj)
+            else:
+                M = np.tile(np.eye(4), (E, 1, 1))
+                if j.jtype == "prismatic":
+                    M[:, :3, 3] = (j.axis / (np.linalg.norm(j.axis) or 1.0))[None, :] * qj[:, None]
+            T[j.child] = T[j.parent] @ j.origin @ M
+        return T
+
+    def body_poses(self, q: np.ndarray, n_links: Optional[int] = None) -> np.ndarray:
+        """[E, B, 7] fp64 (wxyz | xyz) of the mesh-carrying bodies (first n_links of them)."""
+        from .transforms import SO3
+
+        T = self.link_fk(q)
+        bodies = self.bodies if n_links is None else self.bodies[:n_links]
+        E = next(iter(T.values())).shape[0]
+        out = np.empty((E, len(bodies), 7), dtype=np.float64)
+        for b, name in enumerate(bodies):
+            out[:, b, 4:] = T[name][:, :3, 3]
+            out[:, b, :4] = np.stack([SO3.from_matrix(R).wxyz for R in T[name][:, :3, :3]])
+        return out
+
+
 def visual_fk_from_config(urdf_path: str, joint_config: Sequence[float]) -> List[np.ndarray]:
     u = SimpleURDF.load(urdf_path)
     return u.visual_mesh_fk(dict(zip(u.actuated_joint_names, [float(v) for v in joint_config])))

@@ -105,6 +105,32 @@ def test_urdf_fk_against_hand_composed_chain(toy):
     np.testing.assert_allclose(vis[2], T2 @ H(rpy(0, 0, 0.3), [0.01, 0, 0]), atol=1e-12)
 
 
+def test_batched_body_pose_source_equals_per_env_fk_and_draw_messages(toy):
+    """SURVEY 8f-1, pose source without Drake: [E,B,7] body poses from batched URDF FK == the per-env draw messages."""
+    from sim_a_splat_b200.urdf_fk import BatchedBodyPoseSource
+
+    u = SimpleURDF.load(f"{toy['package_path']}/{toy['package_name']}urdf/{toy['urdf_name']}")
+    src = BatchedBodyPoseSource(u)
+    assert src.joint_names == ["joint1", "joint2", "joint3"] and src.bodies == ["link_base", "link1", "link2", "gripper"]
+    rng = np.random.default_rng(8)
+    q = rng.uniform(-1.0, 1.0, size=(9, 3)) * np.array([1, 1, 0.1])
+    Tb = src.link_fk(q)
+    for e in range(9):
+        Te = u.link_fk(dict(zip(u.actuated_joint_names, q[e])))
+        for name in u.links:
+            np.testing.assert_allclose(Tb[name][e], Te[name], atol=1e-12)
+    B = src.body_poses(q, n_links=N_LINKS)
+    assert B.shape == (9, N_LINKS, 7)
+    h = _handler(toy)
+    env = FakeManipulatorEnv(toy, seed=0)
+    for e in range(9):
+        env.q = q[e].copy()
+        want = h.body_poses_from_msg(env._generate_draw_msg())
+        np.testing.assert_allclose(B[e, :, 4:], want[:, 4:], atol=1e-12)
+        for l in range(N_LINKS):  # the fake env sends un-normalised quaternions; compare rotations
+            np.testing.assert_allclose(tf.SO3(B[e, l, :4]).as_matrix(), tf.SO3(want[l, :4] / np.linalg.norm(want[l, :4])).as_matrix(), atol=1e-12)
+
+
 # ---------------------------------------------------------------------------------- SplatHandler
 def test_handler_partition_matches_reference_grouping(toy):
     """splat_handler.py:104-143: one splat node per link (overlaps duplicated), background = ~union."""
