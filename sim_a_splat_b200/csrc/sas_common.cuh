@@ -73,6 +73,22 @@ __device__ __forceinline__ float sas_exp_neg(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(nf) << 23));
 }
 
+// The same function for -8 <= x <= 0 (the compositor only evaluates sigma <= SAS_SIGMA_SKIP): the clamp at -125
+// cannot bind there, so it is dropped -- every remaining operation, and therefore every result bit, is unchanged.
+__device__ __forceinline__ float sas_exp_neg_small(float x) {
+    const float t = x * 1.44269502162933349609375f;
+    const float nf = t + 12582912.0f;
+    const float n = nf - 12582912.0f;
+    const float f = t - n;
+    float p = 0.001327647129073739f;
+    p = fmaf(p, f, 0.009675540961325169f);
+    p = fmaf(p, f, 0.05550713092088699f);
+    p = fmaf(p, f, 0.24022120237350464f);
+    p = fmaf(p, f, 0.6931469440460205f);
+    p = fmaf(p, f, 1.0000001192092896f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(nf) << 23));
+}
+
 __device__ __forceinline__ void sas_cp_async16(void *smem_dst, const void *gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");

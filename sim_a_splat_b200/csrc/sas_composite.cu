@@ -41,10 +41,12 @@ __device__ __forceinline__ unsigned char to_u8(float v) {
 }
 
 struct Pixel {
-    float pxf, pyf;            // pixel centre
+    float pxf, pyf;            // pixel centre; pxf = NaN once the pixel has finished (every sigma then fails its
+                               // range test by itself: no separate flag to test in the walk loop)
     float T, ar, ag, ab, ad;   // transmittance and accumulators
     int nc;
-    bool done;
+    __device__ __forceinline__ bool done() const { return p_isnan(pxf); }
+    static __device__ __forceinline__ bool p_isnan(float v) { return v != v; }
 };
 
 // Blend staged record j into this lane's pixel (gsplat rasterize_to_pixels inner body).
@@ -53,12 +55,12 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
     const float2 B = *reinterpret_cast<const float2 *>(&sb[j].b);  // conic c / 2, opacity
     const float dx = A.x - p.pxf, dy = A.y - p.pyf;
     const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
-    if (!p.done && sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {
-        const float al = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg(-sigma));
+    if (sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {  // false for a finished pixel (NaN)
+        const float al = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg_small(-sigma));
         if (al >= SAS_ALPHA_MIN) {
             const float nT = p.T * (1.0f - al);
             if (nT <= SAS_T_MIN) {
-                p.done = true;
+                p.pxf = __int_as_float(0x7fc00000);
             } else {
                 const float4 Cc = sb[j].c;
                 const float vis = al * p.T;
@@ -92,7 +94,7 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigne
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3;
     for (int j0 = 0; j0 < cnt; j0 += 32) {
-        const unsigned dm = __ballot_sync(0xffffffffu, p.done);
+        const unsigned dm = __ballot_sync(0xffffffffu, p.done());
         if (dm == 0xffffffffu) break;
         unsigned mask;
         if (MODE == 2) {
@@ -238,10 +240,10 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         const bool group_static = ((dyn_mask >> (warp * 4 + grp)) & 1u) == 0u;
         const float X0 = (float)fx + 0.5f, Y0 = (float)fy + 0.5f;
         Pixel p;
-        p.pxf = (float)px + 0.5f; p.pyf = (float)py + 0.5f;
+        p.pxf = (!inside || group_static) ? __int_as_float(0x7fc00000) : (float)px + 0.5f;
+        p.pyf = (float)py + 0.5f;
         p.T = 1.0f; p.ar = p.ag = p.ab = p.ad = 0.0f;
         p.nc = 0;
-        p.done = !inside || group_static;
 
         // ---- batches: prologue puts batch 0 in flight and the id of batch 1 in a register ----
         const int nb = (n + NT - 1) / NT;
@@ -260,7 +262,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 }
                 s_reach[b & 1][tid] = m;
             }
-            if (__syncthreads_count(p.done) == NT) break;  // also publishes batch b (records and reach masks) to the CTA
+            if (__syncthreads_count(p.done()) == NT) break;  // also publishes batch b (records and reach masks) to the CTA
             const int cnt = min(NT, n - b * NT);
             staged += cnt;
             const int buf = b & 1;
@@ -271,7 +273,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 const int e2 = e1 + NT;
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
-            if (__all_sync(0xffffffffu, p.done)) continue;  // whole warp finished: only keep feeding the pipeline
+            if (__all_sync(0xffffffffu, p.done())) continue;  // whole warp finished: only keep feeding the pipeline
             process_batch<MODE>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp, cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
