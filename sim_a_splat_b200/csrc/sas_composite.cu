@@ -55,7 +55,9 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
     const float2 B = *reinterpret_cast<const float2 *>(&sb[j].b);  // conic c / 2, opacity
     const float dx = A.x - p.pxf, dy = A.y - p.pyf;
     const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
-    if (sigma >= 0.0f && sigma <= SAS_SIGMA_SKIP) {  // false for a finished pixel (NaN)
+    // 0 <= sigma <= SAS_SIGMA_SKIP as ONE unsigned compare of the bit pattern: negative values and NaN (a finished
+    // pixel) have larger patterns; sigma is never -0.0 (its last term (c/2 dy) dy is >= +0)
+    if (__float_as_uint(sigma) <= __float_as_uint(SAS_SIGMA_SKIP)) {
         const float al = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg_small(-sigma));
         if (al >= SAS_ALPHA_MIN) {
             const float nT = p.T * (1.0f - al);
