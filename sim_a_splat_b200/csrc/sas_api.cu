@@ -49,6 +49,7 @@ struct sas_renderer {
     DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
     cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
+    cudaEvent_t scan_ev[3] = {};                      // fork / two joins of the scan + work-list chains
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -242,6 +243,7 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(cudaEventCreateWithFlags(&r->cams_copied, cudaEventDisableTiming));
     for (cudaStream_t &s : r->aux) SAS_CUDA_C(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (cudaEvent_t &ev : r->fork_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaEvent_t &ev : r->scan_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
     long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
@@ -264,6 +266,8 @@ void sas_destroy(sas_renderer *r) {
     for (cudaEvent_t ev : r->stage_ev)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : r->fork_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : r->scan_ev)
         if (ev) cudaEventDestroy(ev);
     if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
     for (cudaStream_t s : r->aux)
@@ -425,7 +429,7 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     if ((rc = ensure(r, r->row_tile_cursor, RT * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_offset, (RT + 1) * 4))) return rc;
     if ((rc = ensure(r, r->img_tile_offset, (IT + 1) * 4))) return rc;
-    if ((rc = ensure(r, r->block_sums, (RT / 1024 + 2) * 4))) return rc;
+    if ((rc = ensure(r, r->block_sums, 2 * (RT / 1024 + 2) * 4))) return rc;  // one half per scan (they run concurrently)
     if ((rc = ensure(r, r->img_max, (size_t)n_images * 4))) return rc;
     if ((rc = ensure(r, r->dyn_mask, IT * 4))) return rc;
     // work lists (sas_work.cu) and the per-view tile buffers shared by the images of a view
@@ -478,12 +482,27 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
                                                 work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p, (int *)r->comp_list.p, st,
                                                 &launches));
     } else {
-        SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
-                                    &launches));
-        SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, (unsigned *)r->block_sums.p, r->counters, r->max_isects, st,
-                                    &launches));
+        // The two scans and the work lists only read the counts (and the group masks): three independent chains of
+        // 3 + 3 + 4 small kernels.  Forked onto side streams they cost the longest chain instead of the sum
+        // (SAS_VARIANT bit 2, as for the sort classes); all three are joined before the emission.
+        unsigned *bs_a = (unsigned *)r->block_sums.p, *bs_b = bs_a + (RT / 1024 + 2);
+        const bool fork = (sas_variant_flags() & 4) != 0;
+        cudaStream_t s_b = fork ? r->aux[0] : st, s_w = fork ? r->aux[1] : st;
+        if (fork) {
+            SAS_CUDA(r, cudaEventRecord(r->scan_ev[0], st));
+            SAS_CUDA(r, cudaStreamWaitEvent(s_b, r->scan_ev[0], 0));
+            SAS_CUDA(r, cudaStreamWaitEvent(s_w, r->scan_ev[0], 0));
+        }
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, bs_a, r->counters, r->max_isects, st, &launches));
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, bs_b, r->counters, r->max_isects, s_b, &launches));
         SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, work, (unsigned char *)r->view_needed.p,
-                                          (int *)r->sort_list.p, (int *)r->comp_list.p, st, &launches));
+                                          (int *)r->sort_list.p, (int *)r->comp_list.p, s_w, &launches));
+        if (fork) {
+            SAS_CUDA(r, cudaEventRecord(r->scan_ev[1], s_b));
+            SAS_CUDA(r, cudaEventRecord(r->scan_ev[2], s_w));
+            SAS_CUDA(r, cudaStreamWaitEvent(st, r->scan_ev[1], 0));
+            SAS_CUDA(r, cudaStreamWaitEvent(st, r->scan_ev[2], 0));
+        }
     }
     SAS_STAGE(2);
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
