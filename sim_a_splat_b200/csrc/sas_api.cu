@@ -50,6 +50,7 @@ struct sas_renderer {
     cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     cudaEvent_t scan_ev[3] = {};                      // fork / two joins of the scan + work-list chains
+    cudaEvent_t span_ev[2] = {};                      // fork / join of the background span next to the link span
     DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
     long long max_isects = 0;
     SasCounters *counters = nullptr;
@@ -244,6 +245,7 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     for (cudaStream_t &s : r->aux) SAS_CUDA_C(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (cudaEvent_t &ev : r->fork_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (cudaEvent_t &ev : r->scan_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaEvent_t &ev : r->span_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
     long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
@@ -268,6 +270,8 @@ void sas_destroy(sas_renderer *r) {
     for (cudaEvent_t ev : r->fork_ev)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : r->scan_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : r->span_ev)
         if (ev) cudaEventDestroy(ev);
     if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
     for (cudaStream_t s : r->aux)
@@ -469,13 +473,26 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
 
 #define SAS_STAGE(i) do { if (r->stage_timing) SAS_CUDA(r, cudaEventRecord(r->stage_ev[i], st)); } while (0)
     SAS_STAGE(0);
+    // The background span (once per view) and the link span (once per image) touch disjoint rows: with both present
+    // the small one runs on a side stream next to the other (projection here, emission below).
+    const bool two_spans = span_bg.n > 0 && span_dy.n > 0 && (sas_variant_flags() & 4);
+    auto fork_span = [&]() -> cudaError_t {
+        cudaError_t e = cudaEventRecord(r->span_ev[0], st);
+        return e != cudaSuccess ? e : cudaStreamWaitEvent(r->aux[2], r->span_ev[0], 0);
+    };
+    auto join_span = [&]() -> cudaError_t {
+        cudaError_t e = cudaEventRecord(r->span_ev[1], r->aux[2]);
+        return e != cudaSuccess ? e : cudaStreamWaitEvent(st, r->span_ev[1], 0);
+    };
+    if (two_spans) SAS_CUDA(r, fork_span());
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
         SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
                                        r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (unsigned *)r->radii.p, rcount,
-                                       sp.row0 == C ? dyn_mask : nullptr, r->counters, st));
+                                       sp.row0 == C ? dyn_mask : nullptr, r->counters, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
         launches += 1;
     }
+    if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(1);
     if (sas_scan_lists_fused_ok(C, I, T)) {
         SAS_CUDA(r, sas_launch_scan_lists_fused(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, roff, ioff, r->counters, r->max_isects,
@@ -505,11 +522,13 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
         }
     }
     SAS_STAGE(2);
+    if (two_spans) SAS_CUDA(r, fork_span());
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
-        SAS_CUDA(r, sas_launch_emit(bins, sp, tw, th, roff, rcursor, pairs, r->max_isects, st));
+        SAS_CUDA(r, sas_launch_emit(bins, sp, tw, th, roff, rcursor, pairs, r->max_isects, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
         launches += 1;
     }
+    if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(3);
     SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, r->aux, r->fork_ev,
                                      &launches));
