@@ -1,32 +1,37 @@
 // sas_composite.cu -- K6: per-tile front-to-back alpha compositing of RGB + depth + alpha
 // (gsplat 1.5.2 rasterize_to_pixels, RGB+ED), and the splatfacto get_outputs post-processing.
 //
-// Persistent CTAs (256 threads, grid = SMs x resident CTAs) pull 16x16 tiles from the work list of
-// sas_work.cu, heaviest first.  Two kinds of item: an image tile whose link bucket is non-empty is
-// composited from its merged (background + link) list into the image; a view tile is the
-// background-only list of a camera, composited once into the per-view buffers and afterwards copied
-// (copy_static_tiles_kernel) into every image of that view whose link bucket for the tile is empty
-// -- those pixels are bit-identical by construction.
+// Persistent CTAs (256 threads, grid = SMs x 8 resident CTAs, 32 registers) pull 16x16 tiles from the
+// work list of sas_work.cu, heaviest first.  Two kinds of item: an image tile whose link bucket is
+// non-empty is composited from its merged (background + link) list into the image; a view tile is
+// the background-only list of a camera, composited once into the per-view buffers and afterwards
+// copied (copy_static_tiles_kernel) into every image of that view whose link bucket for the tile
+// is empty, and into the 4x2-pixel groups of the other tiles that no link Gaussian can reach
+// (tile_dyn_mask, from the projection kernel) -- those pixels are bit-identical by construction.
 //
-// Within a tile each warp owns an 8x4 pixel footprint, one pixel per lane.  The depth-sorted ids
-// are consumed in batches of 256: every thread gathers one 48 B projected record into shared memory
-// with three 16 B cp.async copies (double buffered, the id for the batch after next prefetched into
-// a register), so global latency overlaps the arithmetic of the current batch.  Inside a batch each
-// warp first tests 32 Gaussians at once (one per lane) against its footprint using the record's
-// screen-space extents, ballots the hits, and only walks the set bits -- in order, so front-to-back
-// order is preserved.  A lane stops when T*(1-alpha) <= 1e-4; a warp skips once all its lanes
-// stopped; the CTA leaves the tile when __syncthreads_count says all 256 pixels stopped.
+// Within a tile each warp owns an 8x4 pixel footprint and each of its four 8-lane groups one 4x2
+// block of it, one pixel per lane.  The depth-sorted ids are consumed in batches of 256: every
+// thread gathers one 48 B projected record into shared memory with three 16 B cp.async copies
+// (double buffered, the id for the batch after next prefetched into a register), so global latency
+// overlaps the arithmetic of the current batch; the thread that staged a record also computes, once
+// for the whole CTA, the 32-bit mask of the tile's groups the record's culling extents reach.
+// Inside a batch a warp takes 32 records at a time, ballots its four mask bits (one hit mask per
+// group), and every group walks only its own hits -- in order, so front-to-back order is preserved.
+// A lane stops when T*(1-alpha) <= 1e-4 (its pixel centre becomes NaN, which fails every later
+// range test by itself); a group / warp skips once all its lanes stopped; the CTA leaves the tile
+// when __syncthreads_count says all 256 pixels stopped.
 //
-// The footprint test is conservative: the extents (sas_project.cu) bound the region where
+// The reach test is conservative: the extents (sas_project.cu) bound the region where
 // alpha >= 1/255 is possible -- a pixel with |dx| > ex has sigma >= dx^2/(2 cov_xx) > ln(255*opacity),
 // i.e. alpha < 1/255, so the reference rule would have skipped it as well (the extents carry a
 // margin far above the rounding of sigma).  Likewise sigma > SAS_SIGMA_SKIP skips the exp.  Neither
 // changes any output bit.
 //
-// Not bandwidth bound: FP32 issue bound (sigma, the polynomial exp, 4 FMA accumulations).
-// (An mbarrier ring that let warps drift 1-2 batches apart instead of meeting at a barrier every
-// batch was measured at -0 % .. -4 % and dropped: the time is in issued instructions, not in the
-// barrier; see DESIGN.md "Experiments".)
+// Not bandwidth bound.  55 % of the warp-stall samples are the per-batch barrier: the CTA waits for
+// the warp over the densest 4x2 block, whose dependent sigma -> exp -> alpha -> T chain is the
+// critical path; the walk loop is sensitive to its own instruction count (trimmed: no finished-flag
+// test, clamp-free exp, one-compare range test), the test phase and the scheduler balance are not.
+// DESIGN.md "What bounds the compositor" and "Experiments that did not pay" list what was measured.
 #include "sas_common.cuh"
 
 #include <cstdlib>
