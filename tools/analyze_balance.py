@@ -61,14 +61,31 @@ def main():
                     h = h.copy(); h[stop:] = False
                     hp = np.zeros(nch * 32, dtype=np.int32); hp[:n] = h
                     blk[cx, ry] = hp.reshape(nch, 32).sum(1)
-            for name, fn in schemes.items():
+            # dynamic blocks packed densely into warps (k-th dynamic block in sas_group_bit order -> slot k)
+            def bit_of(cx, ry):
+                return ((ry >> 1) * 2 + (cx >> 1)) * 4 + (ry & 1) * 2 + (cx & 1)
+            dyn_bits = sorted(bit_of(cx, ry) for cx in range(4) for ry in range(8) if blk[cx, ry].any())
+            slot_of = {b: k for k, b in enumerate(dyn_bits)}
+            nxt = [len(dyn_bits)]
+            def packed(cx, ry):
+                b = bit_of(cx, ry)
+                if b in slot_of:
+                    k = slot_of[b]
+                else:
+                    k = nxt[0]; nxt[0] += 1
+                return (k >> 2, k & 3)
+            for name, fn in list(schemes.items()) + [("packed dynamic blocks", packed)]:
+                nxt[0] = len(dyn_bits)
+                res.setdefault(name, [0, 0])
                 wcost = np.zeros((8, 4, nch), dtype=np.int32)
                 for cx in range(4):
                     for ry in range(8):
                         w, g = fn(cx, ry)
                         wcost[w, g] += blk[cx, ry]
                 per_warp_chunk = wcost.max(1)                       # chunk-synchronous groups
-                per_warp_batch = per_warp_chunk.reshape(8, nb, 8).sum(2) + 8 * 2   # + test phase ~ 2 walk-equivalents per chunk
+                per_warp_batch = per_warp_chunk.reshape(8, nb, 8).sum(2)
+                warp_has_dyn = wcost.sum((1, 2)) > 0
+                per_warp_batch = per_warp_batch + (8 * 1) * warp_has_dyn[:, None]   # test phase ~ 1 walk-equivalent per chunk, skipped by idle warps
                 res[name][0] += int(per_warp_batch.max(0).sum())
                 res[name][1] += int(per_warp_batch.sum())
     for name, (mx, tot) in res.items():
