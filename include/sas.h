@@ -176,7 +176,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out);
 #define SAS_DBG_TILE_OFFSETS 3 /* [I*T+1] i32 exclusive scan of the merged per-(image,tile) counts = gsplat isect_offsets */
 #define SAS_DBG_SORTED_GIDS 4  /* [M] i32 canonical Gaussian index per intersection, (image,tile,depth,gid) order */
 #define SAS_DBG_VIEW_OF_IMAGE 5 /* [I] i32 */
-#define SAS_DBG_RADII 6     /* same rows as the records, u32: radius_x | radius_y << 16 (gsplat radii; undefined where culled) */
+#define SAS_DBG_RADII 6     /* same rows as the records, [.,2] i32: radius_x, radius_y (gsplat radii; undefined where culled) */
 #define SAS_DBG_LINK_POSES 7 /* [n_envs, L, 12] f32: the link poses in effect (as set, or as composed from body poses) */
 int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes);
 

@@ -237,7 +237,8 @@ static void project_one(const orc_scene *s, int g, const float *pose, const floa
     if (rx <= 0.0f && ry <= 0.0f) return;
     if (m2x + rx <= 0.0f || m2x - rx >= (float)W || m2y + ry <= 0.0f || m2y - ry >= (float)H) return;
 
-    radii[0] = (int32_t)rx; radii[1] = (int32_t)ry;
+    /* saturating conversion (a screen-filling Gaussian a few millimetres from the camera can exceed int32) */
+    radii[0] = (int32_t)fminf(rx, 2147483520.0f); radii[1] = (int32_t)fminf(ry, 2147483520.0f);
     mean2d[0] = m2x; mean2d[1] = m2y; *depth = cz_;
     conic[0] = c / det; conic[1] = -b / det; conic[2] = a / det;
 

@@ -428,7 +428,7 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     int rc;
     if ((rc = ensure(r, r->rec, n_rec * sizeof(SasRecord)))) return rc;
     if ((rc = ensure(r, r->bins, n_rec * sizeof(uint2)))) return rc;
-    if ((rc = ensure(r, r->radii, n_rec * 4))) return rc;
+    if ((rc = ensure(r, r->radii, n_rec * 8))) return rc;
     if ((rc = ensure(r, r->row_tile_count, RT * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_cursor, RT * 4))) return rc;
     if ((rc = ensure(r, r->row_tile_offset, (RT + 1) * 4))) return rc;
@@ -488,7 +488,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
         SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
-                                       r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (unsigned *)r->radii.p, rcount,
+                                       r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (uint2 *)r->radii.p, rcount,
                                        sp.row0 == C ? dyn_mask : nullptr, r->counters, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
         launches += 1;
     }
@@ -695,7 +695,7 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
     switch (what) {
         case SAS_DBG_RECORDS: src = r->rec.p; avail = n_rec * sizeof(SasRecord); break;
         case SAS_DBG_BINS: src = r->bins.p; avail = n_rec * sizeof(uint2); break;
-        case SAS_DBG_RADII: src = r->radii.p; avail = n_rec * 4; break;
+        case SAS_DBG_RADII: src = r->radii.p; avail = n_rec * 8; break;
         case SAS_DBG_TILE_OFFSETS: src = r->img_tile_offset.p; avail = (IT + 1) * 4; break;
         case SAS_DBG_VIEW_OF_IMAGE: src = r->view_of_image; avail = (size_t)r->I * 4; break;
         case SAS_DBG_SORTED_GIDS: {

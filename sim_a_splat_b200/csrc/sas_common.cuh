@@ -221,7 +221,7 @@ cudaError_t sas_launch_scan_lists_fused(const unsigned int *row_tile_count, cons
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
+                               uint2 *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
                                cudaStream_t st);
 cudaError_t sas_bin_init();
 cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,

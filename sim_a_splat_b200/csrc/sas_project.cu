@@ -50,7 +50,7 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
                                             const float4 *__restrict__ scale_link, const float *__restrict__ sh_planes, int n_pad, int g,
                                             size_t ig, const float *__restrict__ link_poses, int L, const SasCamera *__restrict__ cam, int W,
                                             int H, int tile_w, int tile_h, SasRecord *__restrict__ rec, uint2 *__restrict__ bins,
-                                            unsigned int *__restrict__ radii_out, int &x0, int &y0, int &x1, int &y1, float4 &reach) {
+                                            uint2 *__restrict__ radii_out, int &x0, int &y0, int &x1, int &y1, float4 &reach) {
 
     const float4 mo = __ldg(mean_op + g);
     const float4 qq = __ldg(quat + g);
@@ -169,7 +169,7 @@ __device__ __forceinline__ bool project_one(const float4 *__restrict__ mean_op, 
     x0 = min(max(x0, 0), tile_w); x1 = min(max(x1, 0), tile_w);
     y0 = min(max(y0, 0), tile_h); y1 = min(max(y1, 0), tile_h);
     bins[ig] = make_uint2((unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24), __float_as_uint(czm));
-    radii_out[ig] = (unsigned)fminf(rx, 65535.0f) | ((unsigned)fminf(ry, 65535.0f) << 16);
+    radii_out[ig] = make_uint2((unsigned)fminf(rx, 2147483520.0f), (unsigned)fminf(ry, 2147483520.0f));  // saturating, as the oracle
 
     // S3: SH colour, view direction rotated into the link's rest frame
     float dx = mx - cam->campos[0], dy = my - cam->campos[1], dz = mz - cam->campos[2];
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ quat, const float4 *__restrict__ scale_link,
                const float *__restrict__ sh_planes, int n_pad, SasRowSpan span, const float *__restrict__ link_poses, int L,
                const SasCamera *__restrict__ row_cams, int W, int H, int tile_w, int tile_h, SasRecord *__restrict__ rec,
-               uint2 *__restrict__ bins, unsigned int *__restrict__ radii_out, unsigned int *__restrict__ row_tile_count,
+               uint2 *__restrict__ bins, uint2 *__restrict__ radii_out, unsigned int *__restrict__ row_tile_count,
                unsigned int *__restrict__ tile_dyn_mask, SasCounters *counters, int smem_tiles, int smem_masks) {
     extern __shared__ unsigned int s_cnt[];  // [smem_tiles] counts (0 = direct global counting), then [smem_tiles] group masks if smem_masks
     unsigned int *s_mask = s_cnt + smem_tiles;
@@ -330,7 +330,7 @@ project_kernel(const float4 *__restrict__ mean_op, const float4 *__restrict__ qu
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
-                               unsigned int *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
+                               uint2 *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
                                cudaStream_t st) {
     if (span.n <= 0 || span.rows <= 0) return cudaSuccess;
     dim3 grid((span.n + 255) / 256, span.rows);

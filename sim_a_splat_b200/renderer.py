@@ -252,7 +252,7 @@ class SplatRenderer:
         n_rec = C * nbg + I * ndy
         rec_raw = np.empty((n_rec, 12), dtype=np.float32)
         bins_raw = np.empty((n_rec, 2), dtype=np.uint32)
-        radii_raw = np.empty((n_rec, 1), dtype=np.uint32)
+        radii_raw = np.empty((n_rec, 2), dtype=np.uint32)
         offs = np.empty(I * T + 1, dtype=np.int32)
         gids = np.empty(M, dtype=np.int32)
         voi = np.empty(I, dtype=np.int32)
@@ -265,8 +265,7 @@ class SplatRenderer:
             dy = raw[C * nbg:].reshape(I, ndy, raw.shape[1])
             return np.concatenate([bg, dy], axis=1)
 
-        rec, bins, rad = per_image(rec_raw), per_image(bins_raw), per_image(radii_raw)[..., 0]
-        radii = np.stack([rad & 0xffff, rad >> 16], axis=-1).astype(np.int32)
+        rec, bins, radii = per_image(rec_raw), per_image(bins_raw), per_image(radii_raw).astype(np.int32)
         rect = np.stack([bins[..., 0] & 0xff, (bins[..., 0] >> 8) & 0xff, (bins[..., 0] >> 16) & 0xff, bins[..., 0] >> 24], axis=-1).astype(np.int32)
         vis = bins[..., 0] != 0
         tiles = ((rect[..., 2] - rect[..., 0]) * (rect[..., 3] - rect[..., 1])).astype(np.int32)
