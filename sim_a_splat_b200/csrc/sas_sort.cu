@@ -12,7 +12,8 @@
 // Buckets are dispatched by size class (threads and shared-memory footprint = occupancy):
 // <=512 entries (4 warps), <=2048 (8 warps), <=5632 and <=12288 (16 warps) in shared memory;
 // larger buckets run the same passes directly on global memory (ping-pong with a second pair
-// buffer) in one CTA.  Each class is one launch of persistent CTAs that pull bucket ids from the
+// buffer) in one CTA of 32 warps.  (Packed 16-bit histograms that let the <=12288 class run 32 warps
+// were measured slower: the per-pass fixed costs grow with the warp count.)  Each class is one launch of persistent CTAs that pull bucket ids from the
 // class's work list (sas_work.cu), so empty classes cost one near-empty launch.
 //
 // HBM traffic: 8 B read + 8 B written per bucket entry.
@@ -222,8 +223,9 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
                                                                                          SAS_SORT_CAP1, capacity);
     tile_sort_kernel<128, false><<<sms * 16, 128, sort_smem<128>(SAS_SORT_CAP0), s_of[0]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 0,
                                                                                           SAS_SORT_CAP0, capacity);
-    tile_sort_kernel<512, true><<<sms, 512, sizeof(SortShared<512>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0,
-                                                                               capacity);
+    // buckets beyond shared memory: 32 warps per CTA (measured on the 6 M-Gaussian 1080p chunk: sort 26.5 -> 19.5 ms)
+    tile_sort_kernel<1024, true><<<sms, 1024, sizeof(SortShared<1024>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0,
+                                                                                  capacity);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (fork)
         for (int k = 0; k < 4; k++) {
