@@ -5,6 +5,8 @@
 #include "../../include/sas.h"
 #include "sas_common.cuh"
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: stage ranges for nsys / ncu --nvtx filtering
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -471,7 +473,15 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     const SasRowSpan span_bg{0, r->n_bg, C, 0, 0};
     const SasRowSpan span_dy{r->n_bg, r->n_dyn, I, C, (long long)C * r->n_bg};
 
-#define SAS_STAGE(i) do { if (r->stage_timing) SAS_CUDA(r, cudaEventRecord(r->stage_ev[i], st)); } while (0)
+    // stage boundaries: CUDA events when per-stage timing is on, and an NVTX range per stage (host-side enqueue
+    // ranges; with SAS_GRAPH=0 they bracket the launches of each stage in a profiler timeline)
+    static const char *const kStageNames[SAS_N_STAGES] = {"sas:project", "sas:scan+lists", "sas:emit", "sas:sort+merge", "sas:composite", "sas:post"};
+#define SAS_STAGE(i)                                                                   \
+    do {                                                                               \
+        if (r->stage_timing) SAS_CUDA(r, cudaEventRecord(r->stage_ev[i], st));         \
+        if ((i) > 0) nvtxRangePop();                                                   \
+        if ((i) < SAS_N_STAGES) nvtxRangePushA(kStageNames[(i) < SAS_N_STAGES ? (i) : 0]); \
+    } while (0)
     SAS_STAGE(0);
     // The background span (once per view) and the link span (once per image) touch disjoint rows: with both present
     // the small one runs on a side stream next to the other (projection here, emission below).
