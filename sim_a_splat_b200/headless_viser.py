@@ -14,7 +14,11 @@ The reference drives its live render path through these calls only (all in /root
 
 Semantics kept: a splat node registered with a `wxyz` argument is a rigid group whose node transform
 (wxyz, position) moves its Gaussians (mu' = R mu + p, Sigma' = R Sigma R^T); nodes registered without
-one are static background.  The viser protocol carries covariances and DC colours only, so a node's
+one are static background.  A triangle mesh registered with `add_mesh_trimesh` (the reference's robot
+link meshes and T-block, splat_handler.py:190-194, :215-219) is drawn by the browser over the splat; here it
+becomes a rigid group of surface Gaussians in its mean vertex colour (ellipsoids/mesh_utils.py), scaled by
+`scale` and moved by the node transform -- pass `meshes_as_splats=False` to ignore meshes instead.  The viser
+protocol carries covariances and DC colours only, so a node's
 (quaternion, scale) are recovered from its covariances by a symmetric eigendecomposition and its SH is
 degree 0 -- unless the caller passes the richer `quats= / scales= / sh=` keywords (our SplatHandler
 does when the loader has them).  Triangle meshes are accepted and ignored (next).
@@ -96,9 +100,28 @@ class _Scene:
         return node
 
     def add_mesh_trimesh(self, name: str, mesh=None, scale=1.0, wxyz=None, position=None):
-        h = _NodeHandle(self._s, name, wxyz, position)
-        self._s.mesh_handles[name] = h
-        return h
+        verts, faces = getattr(mesh, "vertices", None), getattr(mesh, "faces", None)
+        if mesh is None or verts is None or faces is None or not self._s.meshes_as_splats:
+            h = _NodeHandle(self._s, name, wxyz, position)  # pose bookkeeping only: nothing is drawn
+            self._s.mesh_handles[name] = h
+            return h
+        from .ellipsoids.mesh_utils import TriMesh, mesh_to_gaussians
+
+        rgb = (0.7, 0.7, 0.7)
+        vc = getattr(getattr(mesh, "visual", None), "vertex_colors", None)
+        if vc is not None and len(vc):
+            vc = np.asarray(vc, dtype=np.float64)[:, :3]
+            rgb = tuple((vc.mean(0) / (255.0 if vc.max() > 1.0 else 1.0)).tolist())
+        tm = TriMesh(np.asarray(verts, dtype=np.float64) * float(scale), faces)
+        a, b, c = tm.vertices[tm.faces[:, 0]], tm.vertices[tm.faces[:, 1]], tm.vertices[tm.faces[:, 2]]
+        area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1).sum()
+        n = int(np.clip(area / (self._s.mesh_gaussian_spacing ** 2), 200, 20000))
+        means, quats, scales, opac, sh = mesh_to_gaussians(tm, n, rgb=rgb, seed=len(self._s.nodes))
+        node = _SplatNode(self._s, name, means, quats, scales, opac, sh, True,
+                          np.array([1.0, 0.0, 0.0, 0.0]) if wxyz is None else wxyz, position)
+        self._s._add(node)
+        self._s.mesh_handles[name] = node
+        return node
 
 
 class _Camera:
@@ -121,8 +144,11 @@ class _Client:
 class HeadlessViser:
     """Stands where `viser.ViserServer()` stands (splat_handler.py:35-43)."""
 
-    def __init__(self, device: int = 0, background_rgb=(1.0, 1.0, 1.0), max_isects: int = 0):
+    def __init__(self, device: int = 0, background_rgb=(1.0, 1.0, 1.0), max_isects: int = 0, meshes_as_splats: bool = True,
+                 mesh_gaussian_spacing: float = 0.004):
+        """mesh_gaussian_spacing: target distance between the surface Gaussians a mesh is turned into (scene units)."""
         self.scene = _Scene(self)
+        self.meshes_as_splats, self.mesh_gaussian_spacing = bool(meshes_as_splats), float(mesh_gaussian_spacing)
         self.device, self.background_rgb, self._max_isects = device, tuple(float(c) for c in background_rgb), max_isects
         self.nodes: Dict[str, _SplatNode] = {}
         self.mesh_handles: Dict[str, _NodeHandle] = {}

@@ -311,6 +311,32 @@ def test_covariance_decomposition_round_trip():
     assert np.all(np.linalg.det(R2) > 0.999)
 
 
+def test_injected_meshes_become_rigid_splat_groups():
+    """What the reference's own SplatHandler does with an injected server: add_mesh_trimesh(mesh=trimesh.Trimesh, scale=s)
+    (splat_handler.py:190-194, :215-219) and then handle.wxyz / .position per step (:241-249, :296-310)."""
+    class FakeTrimesh:  # the attributes of trimesh.Trimesh that are read
+        def __init__(self):
+            self.vertices = np.array([[0, 0, 0], [0.2, 0, 0], [0.2, 0.1, 0], [0, 0.1, 0]], dtype=np.float64)
+            self.faces = np.array([[0, 1, 2], [0, 2, 3]])
+            self.visual = type("V", (), {"vertex_colors": np.tile(np.uint8([244, 101, 93, 255]), (4, 1))})()
+
+    srv = HeadlessViser()
+    srv.scene.add_gaussian_splats("/bg", centers=np.zeros((5, 3)), covariances=np.tile(np.eye(3) * 1e-4, (5, 1, 1)),
+                                  rgbs=np.full((5, 3), 0.5), opacities=np.full((5, 1), 0.5))
+    h = srv.scene.add_mesh_trimesh("/obj/mesh_task/t", FakeTrimesh(), scale=0.5)
+    sc = srv.build_scene()
+    assert sc.L == 1 and sc.n_background == 5 and sc.N > 5 + 200
+    m = sc.means[sc.link_id == 0]
+    assert m[:, 0].min() >= -1e-6 and m[:, 0].max() <= 0.1 + 1e-6 and m[:, 1].max() <= 0.05 + 1e-6 and np.abs(m[:, 2]).max() < 1e-6  # scaled by 0.5
+    np.testing.assert_allclose(0.5 + S.C0 * sc.sh[sc.link_id == 0][0, 0], np.array([244, 101, 93]) / 255.0, atol=1e-6)
+    h.wxyz = tf.SO3.from_z_radians(0.3).wxyz
+    h.position = [1.0, 2.0, 3.0]
+    np.testing.assert_allclose(srv.link_poses()[0, 0, 9:], [1, 2, 3], atol=1e-7)
+    off = HeadlessViser(meshes_as_splats=False)
+    h2 = off.scene.add_mesh_trimesh("/m", FakeTrimesh(), scale=1.0)
+    assert "/m" not in off.nodes and h2.wxyz.shape == (4,)
+
+
 def test_viser_protocol_only_nodes_become_degree0_scene():
     """A caller that speaks only the viser protocol (centers, covariances, rgbs, opacities[, wxyz])."""
     srv = HeadlessViser()

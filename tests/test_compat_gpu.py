@@ -146,6 +146,35 @@ def test_task_block_is_rendered_and_follows_its_pose(toy):
     env.close()
 
 
+def test_headless_client_renders_an_injected_mesh():
+    """The viser surface alone (INTEGRATION.md option 1): splats + a trimesh-like mesh node, client.get_render."""
+    from sim_a_splat_b200.headless_viser import HeadlessViser
+
+    class Quad:
+        vertices = np.array([[-0.1, -0.1, 0], [0.1, -0.1, 0], [0.1, 0.1, 0], [-0.1, 0.1, 0]], dtype=np.float64)
+        faces = np.array([[0, 1, 2], [0, 2, 3]])
+        visual = type("V", (), {"vertex_colors": np.tile(np.uint8([30, 200, 40, 255]), (4, 1))})()
+
+    rng = np.random.default_rng(1)
+    srv = HeadlessViser(background_rgb=(0.0, 0.0, 0.0))
+    srv.scene.add_gaussian_splats("/bg", centers=rng.uniform(-0.5, 0.5, size=(400, 3)) + [0, 0, 1.5], covariances=np.tile(np.eye(3) * 4e-4, (400, 1, 1)),
+                                  rgbs=rng.uniform(0.2, 0.9, size=(400, 3)), opacities=np.full((400, 1), 0.6))
+    h = srv.scene.add_mesh_trimesh("/mesh", Quad(), scale=1.0, position=(0.0, 0.0, 1.0))
+    ch = srv.get_clients()[0]
+    img0 = ch.get_render(height=96, width=128, wxyz=np.array([1.0, 0, 0, 0]), position=np.zeros(3))
+    assert img0.shape == (96, 128, 3) and img0.dtype == np.uint8
+    green = (img0[..., 1] > 150) & (img0[..., 0] < 90) & (img0[..., 2] < 100)
+    assert green.sum() > 100 and green[48, 64]                    # the quad faces the camera at the image centre
+    h.position = (0.25, 0.0, 1.0)                                  # node transform moves it to the right (+x)
+    img1 = ch.get_render(height=96, width=128, wxyz=np.array([1.0, 0, 0, 0]), position=np.zeros(3))
+    g1 = (img1[..., 1] > 150) & (img1[..., 0] < 90) & (img1[..., 2] < 100)
+    assert g1.sum() > 100 and not g1[48, 64] and np.nonzero(g1)[1].mean() > np.nonzero(green)[1].mean() + 10
+    ref = oracle.render(srv.splat_scene.as_oracle_dict(), np.eye(4, dtype=np.float32)[None], _K(96, 128, ch.camera.fov)[None], 128, 96,
+                        srv.link_poses(), [0], bg=(0.0, 0.0, 0.0))
+    assert np.sum(img1 != _to_u8(ref["rgb"][0])) == 0
+    srv.stop()
+
+
 def test_device_pose_composition_matches_pose_oracle(toy, assets):
     """sas_set_link_poses_from_bodies (csrc/sas_pose.cu) == oracle/pose_oracle.py:link_transform (pinned to the
     reference's draw_handler by tests/golden/draw_handler.npz), over many envs, incl. un-normalised quaternions."""
