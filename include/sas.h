@@ -42,6 +42,7 @@ extern "C" {
 
 #define SAS_MEM_HOST 0
 #define SAS_MEM_DEVICE 1
+#define SAS_MEM_HOST_ASYNC 2 /* sas_outputs.mem only: host buffers filled without synchronising, see sas_wait_outputs */
 
 #define SAS_TILE 16
 
@@ -79,7 +80,11 @@ typedef struct {
 /* Output buffers of one render call.  Any pointer may be NULL (not produced). */
 typedef struct {
     int32_t mem;            /* SAS_MEM_HOST (pinned or pageable; copied D2H, then the  */
-                            /* stream is synchronised) or SAS_MEM_DEVICE               */
+                            /* stream is synchronised), SAS_MEM_DEVICE, or             */
+                            /* SAS_MEM_HOST_ASYNC (PINNED host buffers; the D2H copies */
+                            /* run on a copy stream of the library out of one of two   */
+                            /* alternating device staging sets and the call returns    */
+                            /* at once: the copy of render k overlaps render k+1)      */
     int32_t nerfstudio_post;/* 1: apply splatfacto get_outputs post-processing:        */
                             /*    rgb=clamp(rgb+(1-alpha)*background,0,1) and          */
                             /*    depth=where(alpha>0,depth,max(depth))  (the          */
@@ -160,6 +165,13 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
  * model.get_outputs_for_camera (nerfstudio_utils.py:166-172): renders every image
  * set by sas_set_cameras with the current link poses. */
 int sas_render(sas_renderer *r, const sas_outputs *out, void *stream);
+
+/* Blocks until the host buffers of a SAS_MEM_HOST_ASYNC render are complete: age 0 = the latest such render, 1 = the
+ * one before it (older ones have completed by construction: a staging set is only reused after its copy drained).
+ * The reference's counterpart is the blocking return of client.get_render (splat_env_wrapper.py:148-157); the split
+ * into issue + wait lets a vectorised env overlap the observation transfer of step k with the render of step k+1.
+ * At most two async renders may be outstanding, and their host buffers must differ. */
+int sas_wait_outputs(sas_renderer *r, int age);
 
 /* Grow the intersection buffers (pairs, sorted ids) to hold max_isects entries.  A render whose
  * intersection count exceeded the capacity sets sas_stats.overflow; reserve more and re-render. */

@@ -14,6 +14,7 @@ from . import _build
 SAS_OK = 0
 SAS_MEM_HOST = 0
 SAS_MEM_DEVICE = 1
+SAS_MEM_HOST_ASYNC = 2
 SAS_DBG_RECORDS = 1
 SAS_DBG_BINS = 2
 SAS_DBG_TILE_OFFSETS = 3
@@ -24,7 +25,7 @@ SAS_DBG_LINK_POSES = 7
 
 EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
-    "sas_set_pose_model", "sas_set_link_poses_from_bodies", "sas_unproject_depth",
+    "sas_set_pose_model", "sas_set_link_poses_from_bodies", "sas_unproject_depth", "sas_wait_outputs",
     "sas_get_stats", "sas_set_stage_timing", "sas_get_stage_ms", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
 ]
 
@@ -98,6 +99,8 @@ def load(build_if_missing: bool = True):
     lib.sas_set_cameras.restype = C.c_int
     lib.sas_render.argtypes = [P, C.POINTER(Outputs), P]
     lib.sas_render.restype = C.c_int
+    lib.sas_wait_outputs.argtypes = [P, C.c_int]
+    lib.sas_wait_outputs.restype = C.c_int
     lib.sas_reserve_isects.argtypes = [P, C.c_longlong]
     lib.sas_reserve_isects.restype = C.c_int
     lib.sas_get_stats.argtypes = [P, C.POINTER(Stats)]

@@ -53,7 +53,12 @@ struct sas_renderer {
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     cudaEvent_t scan_ev[3] = {};                      // fork / two joins of the scan + work-list chains
     cudaEvent_t span_ev[2] = {};                      // fork / join of the background span next to the link span
-    DevBuf o_rgb, o_depth, o_alpha, o_u8, o_nc;  // device staging when the caller's outputs are host memory
+    // device staging when the caller's outputs are host memory; set [1] only for SAS_MEM_HOST_ASYNC, which alternates
+    // between the two so that the D2H copy of one render overlaps the next render
+    DevBuf o_rgb[2], o_depth[2], o_alpha[2], o_u8[2], o_nc[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t render_done[2] = {}, copy_done[2] = {};
+    unsigned long long async_seq = 0;    // async renders issued so far; render k uses staging set k & 1
     long long max_isects = 0;
     SasCounters *counters = nullptr;
     bool rendered = false;
@@ -68,11 +73,17 @@ struct sas_renderer {
         long long max_isects;
         unsigned long long buf_gen;
     };
-    cudaGraphExec_t graph_exec = nullptr;
-    GraphKey graph_key{};
-    GraphKey pending_key{};          // a graph is only built for a key seen twice in a row
-    bool pending_valid = false;
-    int graph_launches = 0;
+    // two cached graphs (the async host path alternates between two output sets), least recently used replaced
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        GraphKey key{};
+        int launches = 0;
+        unsigned long long used = 0;
+    } graphs[2];
+    GraphKey pending_key[2]{};       // a graph is only built for a key seen before (one of the last two unseen keys)
+    bool pending_valid[2] = {false, false};
+    int pending_next = 0;
+    unsigned long long graph_clock = 0;
     unsigned long long buf_gen = 0;  // bumped whenever a work buffer is (re)allocated: invalidates the graph
     int graph_mode = -1;             // SAS_GRAPH environment variable (default on)
 };
@@ -275,11 +286,18 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : r->span_ev)
         if (ev) cudaEventDestroy(ev);
-    if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
+    for (auto &g : r->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (cudaStream_t s : r->aux)
         if (s) cudaStreamDestroy(s);
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    for (cudaEvent_t ev : r->render_done)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : r->copy_done)
+        if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
-                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb, &r->o_depth, &r->o_alpha, &r->o_u8, &r->o_nc,
+                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_depth[0], &r->o_alpha[0], &r->o_u8[0], &r->o_nc[0],
+                      &r->o_rgb[1], &r->o_depth[1], &r->o_alpha[1], &r->o_u8[1], &r->o_nc[1],
                       &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
@@ -575,20 +593,31 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
     uint8_t *d_u8 = out->rgb_u8;
     int *d_nc = out->n_contrib;
-    const bool host_out = out->mem == SAS_MEM_HOST;
+    if (out->mem != SAS_MEM_HOST && out->mem != SAS_MEM_DEVICE && out->mem != SAS_MEM_HOST_ASYNC)
+        return fail(r, SAS_EINVAL, "sas_render: outputs.mem must be SAS_MEM_HOST, SAS_MEM_DEVICE or SAS_MEM_HOST_ASYNC");
+    const bool async_out = out->mem == SAS_MEM_HOST_ASYNC;
+    const bool host_out = out->mem == SAS_MEM_HOST || async_out;
     const bool ns = out->nerfstudio_post != 0;
+    const int set = async_out ? (int)(r->async_seq & 1u) : 0;  // device staging set of this render
     int rc;
+    if (async_out && !r->copy_stream) {
+        SAS_CUDA(r, cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &ev : r->render_done) SAS_CUDA(r, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : r->copy_done) SAS_CUDA(r, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     if (host_out) {
-        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
-        if (out->depth) { if ((rc = ensure(r, r->o_depth, P * 4))) return rc; d_depth = (float *)r->o_depth.p; }
-        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
-        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8, P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8.p; }
-        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc, P * 4))) return rc; d_nc = (int *)r->o_nc.p; }
+        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb[set], P * 12))) return rc; d_rgb = (float *)r->o_rgb[set].p; }
+        if (out->depth) { if ((rc = ensure(r, r->o_depth[set], P * 4))) return rc; d_depth = (float *)r->o_depth[set].p; }
+        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha[set], P * 4))) return rc; d_alpha = (float *)r->o_alpha[set].p; }
+        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8[set], P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8[set].p; }
+        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc[set], P * 4))) return rc; d_nc = (int *)r->o_nc[set].p; }
     } else if (ns) {
-        if (!d_rgb) { if ((rc = ensure(r, r->o_rgb, P * 12))) return rc; d_rgb = (float *)r->o_rgb.p; }
-        if (!d_alpha) { if ((rc = ensure(r, r->o_alpha, P * 4))) return rc; d_alpha = (float *)r->o_alpha.p; }
+        if (!d_rgb) { if ((rc = ensure(r, r->o_rgb[0], P * 12))) return rc; d_rgb = (float *)r->o_rgb[0].p; }
+        if (!d_alpha) { if ((rc = ensure(r, r->o_alpha[0], P * 4))) return rc; d_alpha = (float *)r->o_alpha[0].p; }
     }
     if ((rc = ensure(r, r->img_max, (size_t)r->I * 4))) return rc;
+    // the render before last used this staging set: its D2H copy must have drained before the set is overwritten
+    if (async_out && r->async_seq >= 2) SAS_CUDA(r, cudaStreamWaitEvent(st, r->copy_done[set], 0));
 
     // The step is ~25 launches, all with arguments that do not change from step to step (link poses and
     // cameras live in fixed device buffers), so it is captured once into a CUDA graph and replayed: one
@@ -607,33 +636,41 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         for (int k = 0; k < 3; k++) key.bg[k] = out->background[k];
         key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc;
         key.max_isects = r->max_isects; key.buf_gen = r->buf_gen;
-        const bool have = r->graph_exec && memcmp(&key, &r->graph_key, sizeof(key)) == 0;
-        if (!have && !(r->pending_valid && memcmp(&key, &r->pending_key, sizeof(key)) == 0)) {
+        sas_renderer::GraphSlot *slot = nullptr;
+        for (auto &g : r->graphs)
+            if (g.exec && memcmp(&key, &g.key, sizeof(key)) == 0) slot = &g;
+        bool seen = false;
+        for (int k = 0; k < 2; k++) seen = seen || (r->pending_valid[k] && memcmp(&key, &r->pending_key[k], sizeof(key)) == 0);
+        if (!slot && !seen) {
             // first sight of this key (e.g. freshly allocated output tensors every call): launch directly and
             // remember it; capturing + instantiating costs more than one step saves
-            memcpy(&r->pending_key, &key, sizeof(key));
-            r->pending_valid = true;
+            memcpy(&r->pending_key[r->pending_next], &key, sizeof(key));
+            r->pending_valid[r->pending_next] = true;
+            r->pending_next ^= 1;
             if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
         } else {
-            if (!have) {
-                if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+            if (!slot) {
+                slot = &r->graphs[0];
+                if (slot->exec && (!r->graphs[1].exec || r->graphs[1].used < slot->used)) slot = &r->graphs[1];
+                if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 SAS_CUDA(r, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
                 rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches);
                 cudaError_t ce = cudaStreamEndCapture(st, &graph);
                 if (rc != SAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess) return fail(r, SAS_ECUDA, std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
-                ce = cudaGraphInstantiate(&r->graph_exec, graph, 0);
+                ce = cudaGraphInstantiate(&slot->exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) {
-                    r->graph_exec = nullptr;
+                    slot->exec = nullptr;
                     return fail(r, SAS_ECUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
                 }
-                memcpy(&r->graph_key, &key, sizeof(key));
-                r->graph_launches = launches;
+                memcpy(&slot->key, &key, sizeof(key));
+                slot->launches = launches;
             }
-            SAS_CUDA(r, cudaGraphLaunch(r->graph_exec, st));
-            launches = r->graph_launches;
+            SAS_CUDA(r, cudaGraphLaunch(slot->exec, st));
+            slot->used = ++r->graph_clock;
+            launches = slot->launches;
         }
     } else {
         if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
@@ -641,13 +678,34 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     r->last_launches = launches;
     r->rendered = true;
     if (host_out) {
-        if (out->rgb) SAS_CUDA(r, cudaMemcpyAsync(out->rgb, d_rgb, P * 12, cudaMemcpyDeviceToHost, st));
-        if (out->depth) SAS_CUDA(r, cudaMemcpyAsync(out->depth, d_depth, P * 4, cudaMemcpyDeviceToHost, st));
-        if (out->alpha) SAS_CUDA(r, cudaMemcpyAsync(out->alpha, d_alpha, P * 4, cudaMemcpyDeviceToHost, st));
-        if (out->rgb_u8) SAS_CUDA(r, cudaMemcpyAsync(out->rgb_u8, d_u8, P * 3, cudaMemcpyDeviceToHost, st));
-        if (out->n_contrib) SAS_CUDA(r, cudaMemcpyAsync(out->n_contrib, d_nc, P * 4, cudaMemcpyDeviceToHost, st));
-        SAS_CUDA(r, cudaStreamSynchronize(st));
+        // async: the copies run on the library's copy stream behind an event, so the caller's stream is free for the
+        // next render; nothing synchronises here (sas_wait_outputs does)
+        cudaStream_t cs = async_out ? r->copy_stream : st;
+        if (async_out) {
+            SAS_CUDA(r, cudaEventRecord(r->render_done[set], st));
+            SAS_CUDA(r, cudaStreamWaitEvent(cs, r->render_done[set], 0));
+        }
+        if (out->rgb) SAS_CUDA(r, cudaMemcpyAsync(out->rgb, d_rgb, P * 12, cudaMemcpyDeviceToHost, cs));
+        if (out->depth) SAS_CUDA(r, cudaMemcpyAsync(out->depth, d_depth, P * 4, cudaMemcpyDeviceToHost, cs));
+        if (out->alpha) SAS_CUDA(r, cudaMemcpyAsync(out->alpha, d_alpha, P * 4, cudaMemcpyDeviceToHost, cs));
+        if (out->rgb_u8) SAS_CUDA(r, cudaMemcpyAsync(out->rgb_u8, d_u8, P * 3, cudaMemcpyDeviceToHost, cs));
+        if (out->n_contrib) SAS_CUDA(r, cudaMemcpyAsync(out->n_contrib, d_nc, P * 4, cudaMemcpyDeviceToHost, cs));
+        if (async_out) {
+            SAS_CUDA(r, cudaEventRecord(r->copy_done[set], cs));
+            r->async_seq++;
+        } else {
+            SAS_CUDA(r, cudaStreamSynchronize(st));
+        }
     }
+    return SAS_OK;
+}
+
+int sas_wait_outputs(sas_renderer *r, int age) {
+    if (!r) return SAS_EINVAL;
+    if (age < 0 || age > 1) return fail(r, SAS_EINVAL, "sas_wait_outputs: age must be 0 (latest async render) or 1 (the one before)");
+    if (r->async_seq <= (unsigned long long)age) return fail(r, SAS_ESTATE, "sas_wait_outputs: no such SAS_MEM_HOST_ASYNC render was issued");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    SAS_CUDA(r, cudaEventSynchronize(r->copy_done[(r->async_seq - 1 - age) & 1u]));
     return SAS_OK;
 }
 

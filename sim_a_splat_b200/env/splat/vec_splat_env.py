@@ -43,7 +43,7 @@ class VecSplatRenderer:
         self._fixed_vm = [c2w_opencv_to_viewmat(v["local_frame"].rotation().wxyz, v["local_frame"].translation()) for v in self.fixed.values()]
         self._static_cameras_set = False
 
-    def render(self, draw_msgs: Sequence, outputs=("rgb_u8",), to_host: bool = True) -> Dict[str, np.ndarray]:
+    def _set_step_inputs(self, draw_msgs: Sequence) -> None:
         assert len(draw_msgs) == self.E
         r = self.renderer
         if r.L:  # draw_handler's algebra runs on the device over all (env, link) at once (csrc/sas_pose.cu)
@@ -58,7 +58,22 @@ class VecSplatRenderer:
                 env += [e] * self.C
             r.set_cameras(np.stack(vms), self.K, self.W, self.H, np.asarray(env, dtype=np.int32))
             self._static_cameras_set = True
-        out = r.render(outputs, background=self.background, to_host=to_host)
+
+    def render(self, draw_msgs: Sequence, outputs=("rgb_u8",), to_host: bool = True) -> Dict[str, np.ndarray]:
+        self._set_step_inputs(draw_msgs)
+        return self._as_obs(self.renderer.render(outputs, background=self.background, to_host=to_host), to_host)
+
+    def render_async(self, draw_msgs: Sequence, outputs=("rgb_u8",)) -> int:
+        """Issue the render of this step's observations and return at once (a ticket for render_wait): the transfer
+        of step k's observations to the host overlaps the render of step k+1 -- the step_async / step_wait split of
+        gymnasium's vector envs.  Issue k+1 before waiting for k; the arrays of k are reused by k+2."""
+        self._set_step_inputs(draw_msgs)
+        return self.renderer.render_async(outputs, background=self.background)
+
+    def render_wait(self, ticket: Optional[int] = None) -> Dict[str, np.ndarray]:
+        return self._as_obs(self.renderer.wait(ticket), True)
+
+    def _as_obs(self, out: dict, to_host: bool) -> Dict[str, np.ndarray]:
         res = {}
         for name, t in out.items():
             a = t.numpy() if to_host else t

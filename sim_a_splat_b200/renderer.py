@@ -165,17 +165,17 @@ class SplatRenderer:
         self.I, self.W, self.H = I, int(width), int(height)
 
     # -- render -----------------------------------------------------------------------------
-    def _alloc(self, name: str, to_host: bool):
+    def _alloc(self, name: str, to_host: bool, slot: int = 0):
         torch = self._torch
         I, H, W = self.I, self.H, self.W
         shape, dt = {"rgb": ((I, H, W, 3), torch.float32), "depth": ((I, H, W), torch.float32),
                      "alpha": ((I, H, W), torch.float32), "rgb_u8": ((I, H, W, 3), torch.uint8),
                      "n_contrib": ((I, H, W), torch.int32)}[name]
         if to_host:
-            t = self._pinned.get(name)
+            t = self._pinned.get((name, slot))
             if t is None or tuple(t.shape) != shape:
                 t = torch.empty(shape, dtype=dt, pin_memory=True)
-                self._pinned[name] = t
+                self._pinned[(name, slot)] = t
             return t
         return torch.empty(shape, dtype=dt, device=f"cuda:{self.device}")
 
@@ -210,6 +210,46 @@ class SplatRenderer:
                     raise L.SasError(-4, "intersection buffers overflowed twice")
         self._handback()
         return {n: bufs[n] for n in names}
+
+    def render_async(self, outputs: Iterable[str] = ("rgb_u8", "depth"), background=(0.0, 0.0, 0.0),
+                     nerfstudio_post: bool = False, stream=None) -> int:
+        """Issue a render into pinned host buffers WITHOUT waiting for it (sas_outputs.mem = SAS_MEM_HOST_ASYNC): the
+        D2H copies run on the library's copy stream out of one of two alternating staging sets, so the transfer of
+        step k overlaps the render of step k+1.  Returns a ticket for wait().  At most two renders may be outstanding
+        (issue k+1, then wait(k)); the tensors wait(k) returned are reused by render k+2.  No overflow check: size
+        max_isects beforehand (stats()['overflow'] after a render tells)."""
+        if self.I == 0:
+            raise RuntimeError("set_cameras has not been called")
+        seq = getattr(self, "_async_seq", 0)
+        names = list(outputs)
+        bufs = {n: self._alloc(n, True, slot=seq & 1) for n in names}
+        o = L.Outputs()
+        o.mem = L.SAS_MEM_HOST_ASYNC
+        o.nerfstudio_post = 1 if nerfstudio_post else 0
+        o.background = (C.c_float * 3)(*[float(b) for b in background])
+        for n in ("rgb", "depth", "alpha", "rgb_u8", "n_contrib"):
+            setattr(o, n, C.c_void_p(bufs[n].data_ptr()) if n in bufs else None)
+        L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), self._stream(stream)))
+        self._handback()
+        if not hasattr(self, "_async_bufs"):
+            self._async_bufs = [None, None]
+        self._async_bufs[seq & 1] = bufs
+        self._async_seq = seq + 1
+        return seq
+
+    def wait(self, ticket: Optional[int] = None) -> dict:
+        """Block until the host buffers of render_async ticket (default: the latest) are complete; returns them."""
+        seq = getattr(self, "_async_seq", 0)
+        if ticket is None:
+            ticket = seq - 1
+        age = seq - 1 - ticket
+        if seq == 0 or age < 0:
+            raise RuntimeError("wait(): no such render_async ticket")
+        if age <= 1:  # older renders have completed by construction (their staging set was reused since)
+            L.check(self._lib, self._h, self._lib.sas_wait_outputs(self._h, int(age)))
+        else:
+            raise RuntimeError("wait(): the buffers of this ticket have been reused by a later render_async")
+        return self._async_bufs[ticket & 1]
 
     def reserve_isects(self, n: int) -> None:
         L.check(self._lib, self._h, self._lib.sas_reserve_isects(self._h, int(n)))
