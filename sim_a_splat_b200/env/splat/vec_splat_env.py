@@ -14,15 +14,18 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ...renderer import SplatRenderer
+from ...renderer import PipelinedSplatRenderer, SplatRenderer
 from ...scene import c2w_opencv_to_viewmat
 from ...splat.splat_handler import SplatHandler
 
 
 class VecSplatRenderer:
     def __init__(self, handler: SplatHandler, camera_setup_info: dict, n_envs: int, fov: float = np.radians(75.0),
-                 background=(1.0, 1.0, 1.0), device: int = 0, max_isects: int = 0, env_range: Optional[range] = None):
-        """env_range: the envs this process renders (multi-GPU sharding, see sim_a_splat_b200/dist.py)."""
+                 background=(1.0, 1.0, 1.0), device: int = 0, max_isects: int = 0, env_range: Optional[range] = None,
+                 pipeline_depth: int = 0):
+        """env_range: the envs this process renders (multi-GPU sharding, see sim_a_splat_b200/dist.py).
+        pipeline_depth > 0: render_async / render_wait keep that many steps in flight on as many renderer handles
+        (PipelinedSplatRenderer); render() is then not available."""
         self.handler, self.info, self.fov, self.background = handler, camera_setup_info, fov, background
         self.envs = list(env_range) if env_range is not None else list(range(n_envs))
         self.moving = {k: v for k, v in camera_setup_info.items() if v.get("type") == "moving"}
@@ -34,8 +37,8 @@ class VecSplatRenderer:
         self.H, self.W = (int(v) for v in sizes.pop())
         scene = handler.server.build_scene()
         self.E, self.C = len(self.envs), len(self.keys)
-        self.renderer = SplatRenderer(scene, device=device, max_images=self.E * self.C, max_envs=self.E, max_width=self.W,
-                                      max_height=self.H, max_isects=max_isects)
+        kw = dict(device=device, max_images=self.E * self.C, max_envs=self.E, max_width=self.W, max_height=self.H, max_isects=max_isects)
+        self.renderer = PipelinedSplatRenderer(scene, depth=pipeline_depth, **kw) if pipeline_depth > 0 else SplatRenderer(scene, **kw)
         fy = self.H / (2.0 * np.tan(fov / 2.0))
         self.K = np.array([[fy, 0, self.W / 2.0], [0, fy, self.H / 2.0], [0, 0, 1.0]])
         if self.renderer.L:
@@ -56,10 +59,15 @@ class VecSplatRenderer:
                     vms.append(c2w_opencv_to_viewmat(wxyz, xyz))
                 vms += self._fixed_vm
                 env += [e] * self.C
-            r.set_cameras(np.stack(vms), self.K, self.W, self.H, np.asarray(env, dtype=np.int32))
+            if isinstance(r, PipelinedSplatRenderer):  # moving cameras belong to the step, fixed ones to every handle
+                r.set_cameras(np.stack(vms), self.K, self.W, self.H, np.asarray(env, dtype=np.int32), current_only=bool(self.moving))
+            else:
+                r.set_cameras(np.stack(vms), self.K, self.W, self.H, np.asarray(env, dtype=np.int32))
             self._static_cameras_set = True
 
     def render(self, draw_msgs: Sequence, outputs=("rgb_u8",), to_host: bool = True) -> Dict[str, np.ndarray]:
+        if isinstance(self.renderer, PipelinedSplatRenderer):
+            raise RuntimeError("pipeline_depth > 0: use render_async / render_wait")
         self._set_step_inputs(draw_msgs)
         return self._as_obs(self.renderer.render(outputs, background=self.background, to_host=to_host), to_host)
 

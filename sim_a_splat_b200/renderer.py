@@ -326,3 +326,112 @@ class SplatRenderer:
             isect_ids=isect_ids, flatten_ids=flat.astype(np.int32), isect_offsets=offs[:-1].reshape(I, th, tw).copy(),
             M=M, tile_bits=tile_bits, stats=s, view_of_image=voi,
         )
+
+
+class PipelinedSplatRenderer:
+    """`depth` SplatRenderers (each its own libsas handle, work buffers and CUDA stream) used round-robin, so that
+    consecutive steps overlap on the device as well as on the copy engines: while step k composites (its tail is the
+    latency of the heaviest tile's blend chain), step k+1 already projects, bins and sorts on the
+    SMs the compositor no longer fills, and step k-1's observations travel to the host.  Every step still does all of
+    its own work; the images are bit-identical to SplatRenderer's (tests/test_gpu_parity.py).
+
+    Use: set_cameras once; per step set_link_poses(...) (or set_link_poses_from_bodies) then render_async() -> ticket;
+    wait(ticket) returns that step's pinned host tensors.  Keep at most `depth` steps outstanding: issue step k+1,
+    then wait for step k.  The tensors of step k are reused by step k + 2*depth.
+
+    The reference has no counterpart (it blocks on one browser round trip per camera,
+    /root/reference/sim_a_splat/env/splat/splat_env_wrapper.py:147-158); this is the step_async / step_wait split of
+    vectorised envs applied to the observation render.  The scene is held once per handle (27-70 MB for the
+    reference's scenes)."""
+
+    def __init__(self, scene: SplatScene, depth: int = 2, device: int = 0, **kw):
+        import torch
+
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self._torch = torch
+        self.device = int(device)
+        self.renderers = [SplatRenderer(scene, device=device, **kw) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        self.depth, self.L, self.N = depth, scene.L, scene.N
+        self._seq = 0          # steps issued so far; step k runs on renderer k % depth
+        self._sub = {}         # ticket -> sub-renderer ticket
+
+    def _cur(self):
+        k = self._seq % self.depth
+        return self.renderers[k], self.streams[k]
+
+    def _after_caller(self, s) -> None:
+        s.wait_stream(self._torch.cuda.current_stream(self.device))  # inputs produced on the caller's stream
+
+    def set_cameras(self, viewmats, Ks, width: int, height: int, env_of_image=None, current_only: bool = False) -> None:
+        """Cameras of every handle (fixed cameras: call once), or with current_only=True of the NEXT render_async only
+        (cameras that move with the step: call before each render_async)."""
+        for r, s in [self._cur()] if current_only else zip(self.renderers, self.streams):
+            r.set_cameras(viewmats, Ks, width, height, env_of_image, stream=s)
+
+    def set_pose_model(self, **kw) -> None:
+        for r in self.renderers:
+            r.set_pose_model(**kw)
+
+    def set_link_poses(self, poses) -> None:
+        """Link poses of the NEXT render_async."""
+        r, s = self._cur()
+        self._after_caller(s)
+        r.set_link_poses(poses, stream=s)
+
+    def set_link_poses_from_bodies(self, body_wxyz_xyz) -> None:
+        r, s = self._cur()
+        self._after_caller(s)
+        r.set_link_poses_from_bodies(body_wxyz_xyz, stream=s)
+
+    def render_async(self, outputs: Iterable[str] = ("rgb_u8", "depth"), background=(0.0, 0.0, 0.0),
+                     nerfstudio_post: bool = False) -> int:
+        r, s = self._cur()
+        self._after_caller(s)
+        self._sub[self._seq] = r.render_async(outputs, background=background, nerfstudio_post=nerfstudio_post, stream=s)
+        self._sub.pop(self._seq - 2 * self.depth, None)
+        self._seq += 1
+        return self._seq - 1
+
+    def render(self, outputs: Iterable[str] = ("rgb", "depth", "alpha"), background=(0.0, 0.0, 0.0),
+               nerfstudio_post: bool = False) -> dict:
+        """Device-resident outputs of the next step, enqueued on that step's own stream; returns at once.  The CUDA
+        tensors belong to the handle that drew them (valid until its next render, `depth` steps later) and are ordered
+        on its stream: call join() before consuming them on the caller's stream."""
+        r, s = self._cur()
+        self._after_caller(s)
+        k = self._seq % self.depth
+        names = tuple(outputs)
+        if not hasattr(self, "_dev_out"):
+            self._dev_out = {}
+        bufs = self._dev_out.get((k, names))
+        if bufs is None or any(tuple(b.shape[:3]) != (r.I, r.H, r.W) for b in bufs.values()):
+            bufs = self._dev_out[(k, names)] = {n: r._alloc(n, False) for n in names}
+        r.render(names, background=background, nerfstudio_post=nerfstudio_post, out=bufs, stream=s, check=False)
+        self._seq += 1
+        return bufs
+
+    def join(self) -> None:
+        """Order the caller's current stream after every step issued so far."""
+        cur = self._torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def wait(self, ticket: Optional[int] = None) -> dict:
+        if ticket is None:
+            ticket = self._seq - 1
+        if ticket not in self._sub:
+            raise RuntimeError("wait(): no such render_async ticket (never issued, or its buffers have been reused)")
+        return self.renderers[ticket % self.depth].wait(self._sub[ticket])
+
+    def stats(self) -> dict:
+        """Counters of the most recently issued step's renderer."""
+        return self.renderers[(self._seq - 1) % self.depth].stats()
+
+    def last_launch_count(self) -> int:
+        return self.renderers[(self._seq - 1) % self.depth].last_launch_count()
+
+    def close(self) -> None:
+        for r in self.renderers:
+            r.close()

@@ -97,6 +97,18 @@ def test_vec_renderer_matches_single_env_wrappers(toy):
         for e in range(E):
             assert np.array_equal(out[f"camera_{ci}"][e], singles[e][f"camera_{ci}"]), (ci, e)
     vec.close()
+    # two steps in flight on two handles (render_async / render_wait): same images, whichever handle drew them
+    pv = VecSplatRenderer(handler, cams, n_envs=E, fov=env.ch.camera.fov, background=handler.server.background_rgb, pipeline_depth=2)
+    t0 = pv.render_async(msgs)
+    t1 = pv.render_async(msgs[::-1])
+    a, t2 = pv.render_wait(t0), pv.render_async(msgs)
+    for ci in range(2):
+        assert np.array_equal(a[f"camera_{ci}"], out[f"camera_{ci}"]), ci
+        assert np.array_equal(pv.render_wait(t1)[f"camera_{ci}"], out[f"camera_{ci}"][::-1]), ci
+        assert np.array_equal(pv.render_wait(t2)[f"camera_{ci}"], out[f"camera_{ci}"]), ci
+    with pytest.raises(RuntimeError):
+        pv.render(msgs)
+    pv.close()
     parts = []
     for rank in range(2):
         rng = D.shard_envs(E, 2, rank)

@@ -7,7 +7,7 @@ import torch
 
 import oracle
 from sim_a_splat_b200 import scene as S
-from sim_a_splat_b200.renderer import NS_BACKGROUND, SplatRenderer
+from sim_a_splat_b200.renderer import NS_BACKGROUND, PipelinedSplatRenderer, SplatRenderer
 
 from parity_utils import assert_parity, compare, run_both
 
@@ -257,6 +257,43 @@ def test_async_host_outputs_pipeline_matches_blocking():
     for k in names:
         assert torch.equal(again[k], want[2][k]), k
     r.close()
+
+
+def test_pipelined_renderer_two_steps_in_flight_matches_blocking():
+    """PipelinedSplatRenderer: two handles on two streams used alternately, steps overlap on the device.  Every step's
+    observations equal the single-handle blocking render of the same poses, bit for bit."""
+    sc = S.make_synthetic_scene(15000, 2, seed=33, link_counts=(800, 400))
+    W, H, E = 112, 96, 5
+    vms = np.repeat(S.ring_cameras(1, (0, 0, 0), seed=4), E, axis=0)
+    names = ("rgb_u8", "depth", "n_contrib")
+    poses = [S.random_link_poses(E, 2, seed=60 + k) for k in range(9)]
+    r = SplatRenderer(sc, max_images=E, max_envs=E, max_width=W, max_height=H)
+    r.set_cameras(vms, S.fov_intrinsics(W, H), W, H, np.arange(E))
+    want = []
+    for p in poses:
+        r.set_link_poses(p)
+        want.append({k: v.clone() for k, v in r.render(names, to_host=True).items()})
+    r.close()
+    for depth in (1, 2, 3):
+        pr = PipelinedSplatRenderer(sc, depth=depth, max_images=E, max_envs=E, max_width=W, max_height=H)
+        pr.set_cameras(vms, S.fov_intrinsics(W, H), W, H, np.arange(E))
+        pending = []
+        for i, p in enumerate(poses):
+            pr.set_link_poses(torch.from_numpy(p).cuda() if i % 3 == 0 else p)
+            pending.append((i, pr.render_async(names)))
+            if len(pending) > depth:
+                j, tk = pending.pop(0)
+                got = pr.wait(tk)
+                for k in names:
+                    assert torch.equal(got[k], want[j][k]), (depth, j, k)
+        for j, tk in pending:
+            got = pr.wait(tk)
+            for k in names:
+                assert torch.equal(got[k], want[j][k]), (depth, j, k)
+        assert pr.stats()["overflow"] == 0
+        with pytest.raises(RuntimeError):
+            pr.wait(10_000)
+        pr.close()
 
 
 def test_overflow_is_reported_and_regrown():
