@@ -55,6 +55,8 @@ struct Pixel {
 };
 
 // Blend staged record j into this lane's pixel (gsplat rasterize_to_pixels inner body).
+// COUNT = false drops the per-pixel contributor count (only produced when n_contrib is requested).
+template <bool COUNT>
 __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) {
     const float4 A = sb[j].a;
     const float2 B = *reinterpret_cast<const float2 *>(&sb[j].b);  // conic c / 2, opacity
@@ -67,7 +69,9 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
         if (al >= SAS_ALPHA_MIN) {
             const float nT = p.T * (1.0f - al);
             if (nT <= SAS_T_MIN) {
-                p.pxf = __int_as_float(0x7fc00000);
+                // the pixel has finished.  (asm volatile keeps this a predicated one-instruction block: written as a plain
+                // assignment the compiler forms a select that costs three moves on EVERY blend)
+                asm volatile("mov.b32 %0, 0x7fc00000;" : "=f"(p.pxf));
             } else {
                 const float4 Cc = sb[j].c;
                 const float vis = al * p.T;
@@ -76,7 +80,7 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
                 p.ab = fmaf(Cc.z, vis, p.ab);
                 p.ad = fmaf(Cc.w, vis, p.ad);
                 p.T = nT;
-                p.nc++;
+                if (COUNT) p.nc++;
             }
         }
     }
@@ -96,7 +100,7 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
 //   computed its 32-bit reach mask over all the tile's groups once (s_reach), a warp just ballots its
 //   own four bits (profile of MODE 1: 60 instructions per 32-record chunk per warp in the test phase,
 //   18 % of the kernel's instructions).
-template <int MODE>
+template <int MODE, bool COUNT>
 __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigned *s_reach, int warp, int cnt, Pixel &p, float X0, float Y0) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3;
@@ -142,7 +146,7 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigne
         while (mask) {  // the groups diverge here; no warp-synchronous operation inside
             const int j = __ffs(mask);
             mask &= mask - 1;
-            blend_one(sb1, j, p);
+            blend_one<COUNT>(sb1, j, p);
         }
         __syncwarp();
     }
@@ -170,7 +174,7 @@ __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *sr
 // independent CTAs resident on the SM, not the warps of one CTA.
 __constant__ int sas_variant_flags_dev = 0xff;
 
-template <int WARPS, int MODE>
+template <int WARPS, int MODE, bool COUNT>
 __global__ void __launch_bounds__(WARPS * 32, 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
@@ -281,7 +285,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
             if (__all_sync(0xffffffffu, p.done())) continue;  // whole warp finished: only keep feeding the pipeline
-            process_batch<MODE>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp, cnt, p, X0, Y0);
+            process_batch<MODE, COUNT>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp, cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
 #undef SAS_REC_OF
@@ -380,10 +384,14 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
-#define SAS_COMP(W, M) composite_kernel<W, M><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
+#define SAS_COMP(W, M) composite_kernel<W, M, true><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
     const int mode = (vf & 1) ? ((vf & 64) ? 2 : 1) : 0;
     if (parts == 0) {
-        if (mode == 2) SAS_COMP(8, 2); else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
+        if (mode == 2) {
+            // the default: counts per-pixel contributors only when the caller asked for n_contrib
+            if (img_out.n_contrib) SAS_COMP(8, 2);
+            else composite_kernel<8, 2, false><<<g_comp_sms * 8, 256, 0, st>>>(SAS_ARGS);
+        } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
     } else if (parts == 1) {
         if (mode == 2) SAS_COMP(4, 2); else SAS_COMP(4, 1);
     } else {
