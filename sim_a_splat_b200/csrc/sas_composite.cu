@@ -363,11 +363,13 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 }
 
 int g_comp_sms = 148;
+int g_comp_ctas = 8;  // persistent CTAs per SM of the default compositor (SAS_COMP_CTAS, experiments: 8 is best)
 
 }  // namespace
 
 cudaError_t sas_composite_init(int n_sms) {
     g_comp_sms = n_sms > 0 ? n_sms : 148;
+    if (const char *e = getenv("SAS_COMP_CTAS")) g_comp_ctas = atoi(e) > 0 ? atoi(e) : 8;
     const int vf = sas_variant_flags();
     return cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
 }
@@ -389,8 +391,8 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
     if (parts == 0) {
         if (mode == 2) {
             // the default: counts per-pixel contributors only when the caller asked for n_contrib
-            if (img_out.n_contrib) SAS_COMP(8, 2);
-            else composite_kernel<8, 2, false><<<g_comp_sms * 8, 256, 0, st>>>(SAS_ARGS);
+            if (img_out.n_contrib) composite_kernel<8, 2, true><<<g_comp_sms * g_comp_ctas, 256, 0, st>>>(SAS_ARGS);
+            else composite_kernel<8, 2, false><<<g_comp_sms * g_comp_ctas, 256, 0, st>>>(SAS_ARGS);
         } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
     } else if (parts == 1) {
         if (mode == 2) SAS_COMP(4, 2); else SAS_COMP(4, 1);
