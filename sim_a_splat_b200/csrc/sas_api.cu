@@ -618,6 +618,8 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     if ((rc = ensure(r, r->img_max, (size_t)r->I * 4))) return rc;
     // the render before last used this staging set: its D2H copy must have drained before the set is overwritten
     if (async_out && r->async_seq >= 2) SAS_CUDA(r, cudaStreamWaitEvent(st, r->copy_done[set], 0));
+    // a blocking host render after async ones reuses staging set 0: wait for the async copy that may still read it
+    if (host_out && !async_out && r->async_seq >= 1) SAS_CUDA(r, cudaStreamWaitEvent(st, r->copy_done[0], 0));
 
     // The step is ~25 launches, all with arguments that do not change from step to step (link poses and
     // cameras live in fixed device buffers), so it is captured once into a CUDA graph and replayed: one
