@@ -1,8 +1,9 @@
 // sas_composite.cu -- K6: per-tile front-to-back alpha compositing of RGB + depth + alpha
 // (gsplat 1.5.2 rasterize_to_pixels, RGB+ED), and the splatfacto get_outputs post-processing.
 //
-// Persistent CTAs (256 threads, grid = SMs x 8 resident CTAs, 32 registers) pull 16x16 tiles from the
-// work list of sas_work.cu, heaviest first.  Two kinds of item: an image tile whose link bucket is
+// CTAs (256 threads, 32 registers, 8 resident per SM) pull 16x16 tiles from the work list of sas_work.cu through one
+// atomic counter, heaviest first; a CTA takes SAS_COMP_ITEMS items (default 1; 0 = persistent CTAs, grid = SMs x 8)
+// and exits, the grid holds enough CTAs for every possible item.  Two kinds of item: an image tile whose link bucket is
 // non-empty is composited from its merged (background + link) list into the image; a view tile is
 // the background-only list of a camera, composited once into the per-view buffers and afterwards
 // copied (copy_static_tiles_kernel) into every image of that view whose link bucket for the tile
@@ -180,7 +181,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
                  const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_list, SasWork *work, int n_bg, int n_dyn,
                  int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
-                 SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters) {
+                 SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, int max_items) {
     constexpr int NT = WARPS * 32;     // threads = records per batch
     constexpr int PARTS = 8 / WARPS;   // CTAs per tile
     __shared__ SasRecord stage[2][NT];
@@ -191,7 +192,9 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
     const long long IT = (long long)I * T;
     int staged = 0;
 
-    for (;;) {
+    // max_items: work items a CTA takes before it exits (0 = until the list is empty).  A bounded CTA hands its SM
+    // slot back to the block scheduler, so kernels of another stream can move in while this one is still running.
+    for (int taken = 0; max_items == 0 || taken < max_items; taken++) {
         __syncthreads();  // every thread is done with the previous tile's stage buffers and s_take
         if (tid == 0) s_take = atomicAdd(&work->comp_take, 1u);
         __syncthreads();
@@ -363,12 +366,15 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 }
 
 int g_comp_sms = 148;
+int g_comp_items = 1; // SAS_COMP_ITEMS: work items per compositor CTA before it exits (0 = persistent CTAs); measured on the
+                      // pusht batch: 1 -> 1.208, 2 -> 1.213, 4 -> 1.221, 8 -> 1.235, persistent -> 1.231 ms/step
 int g_comp_ctas = 8;  // persistent CTAs per SM of the default compositor (SAS_COMP_CTAS, experiments: 8 is best)
 
 }  // namespace
 
 cudaError_t sas_composite_init(int n_sms) {
     g_comp_sms = n_sms > 0 ? n_sms : 148;
+    if (const char *e = getenv("SAS_COMP_ITEMS")) g_comp_items = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("SAS_COMP_CTAS")) g_comp_ctas = atoi(e) > 0 ? atoi(e) : 8;
     const int vf = sas_variant_flags();
     return cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
@@ -383,16 +389,22 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
                                  int *n_launches) {
 #define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
-                 tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters
+                 tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
+    int max_items = 0;
 #define SAS_COMP(W, M) composite_kernel<W, M, true><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
     const int mode = (vf & 1) ? ((vf & 64) ? 2 : 1) : 0;
     if (parts == 0) {
         if (mode == 2) {
             // the default: counts per-pixel contributors only when the caller asked for n_contrib
-            if (img_out.n_contrib) composite_kernel<8, 2, true><<<g_comp_sms * g_comp_ctas, 256, 0, st>>>(SAS_ARGS);
-            else composite_kernel<8, 2, false><<<g_comp_sms * g_comp_ctas, 256, 0, st>>>(SAS_ARGS);
+            int grid = g_comp_sms * g_comp_ctas;
+            if (g_comp_items > 0) {  // bounded CTAs: enough of them for every possible item
+                max_items = g_comp_items;
+                grid = max(grid, (int)(((long long)(I + C) * tile_w * tile_h + max_items - 1) / max_items));
+            }
+            if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
+            else composite_kernel<8, 2, false><<<grid, 256, 0, st>>>(SAS_ARGS);
         } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
     } else if (parts == 1) {
         if (mode == 2) SAS_COMP(4, 2); else SAS_COMP(4, 1);
