@@ -392,17 +392,17 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
-    int max_items = 0;
-#define SAS_COMP(W, M) composite_kernel<W, M, true><<<g_comp_sms * (64 / W), W * 32, 0, st>>>(SAS_ARGS)
+    // bounded CTAs (SAS_COMP_ITEMS > 0): enough of them for every possible item; otherwise persistent CTAs
+    const int max_items = g_comp_items;
+    const long long all_items = (long long)(I + C) * tile_w * tile_h;
+#define SAS_GRID(W) (max_items > 0 ? (int)max((long long)g_comp_sms * (64 / (W)), (all_items * (8 / (W)) + max_items - 1) / max_items) \
+                                   : g_comp_sms * (64 / (W)))
+#define SAS_COMP(W, M) composite_kernel<W, M, true><<<SAS_GRID(W), W * 32, 0, st>>>(SAS_ARGS)
     const int mode = (vf & 1) ? ((vf & 64) ? 2 : 1) : 0;
     if (parts == 0) {
         if (mode == 2) {
             // the default: counts per-pixel contributors only when the caller asked for n_contrib
-            int grid = g_comp_sms * g_comp_ctas;
-            if (g_comp_items > 0) {  // bounded CTAs: enough of them for every possible item
-                max_items = g_comp_items;
-                grid = max(grid, (int)(((long long)(I + C) * tile_w * tile_h + max_items - 1) / max_items));
-            }
+            const int grid = max_items > 0 ? SAS_GRID(8) : g_comp_sms * g_comp_ctas;
             if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
             else composite_kernel<8, 2, false><<<grid, 256, 0, st>>>(SAS_ARGS);
         } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
@@ -411,6 +411,7 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
     } else {
         if (mode == 2) SAS_COMP(2, 2); else SAS_COMP(2, 1);
     }
+#undef SAS_GRID
 #undef SAS_COMP
 #undef SAS_ARGS
     dim3 grid(tile_w * tile_h, I);
