@@ -297,8 +297,8 @@ def run_ours(args):
                          "unit": "GB/s", "frac": round(ab[dom] / (stage[dom] * 1e-3) / 1e9 / hbm, 4), "traffic": traffic.get(dom),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this command (profiles/traffic.json)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "note": "the compositor is FP32-issue bound, not HBM bound (DESIGN.md); its GB/s is reported for the contract, "
-                                 "see fp32 and stages for the numbers that explain it"},
+                         "note": "the compositor is bound by the latency of its dependent blend chain, not by HBM (DESIGN.md section 5); its GB/s is "
+                                 "reported for the contract, see fp32 and stages for the numbers that explain it"},
             "roofline_step": {"alg_bytes": int(sum(ab.values())), "achieved": round(sum(ab.values()) / (sum(stage.values()) * 1e-3) / 1e9, 1),
                               "peak": hbm, "unit": "GB/s", "frac": round(sum(ab.values()) / (sum(stage.values()) * 1e-3) / 1e9 / hbm, 4)},
             "stages": stages,
