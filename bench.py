@@ -134,6 +134,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_cpus = None
+    if world > 1 and os.environ.get("SAS_BIND_NUMA", "1") != "0":
+        from sim_a_splat_b200.dist import bind_to_gpu_numa
+
+        numa_cpus = bind_to_gpu_numa(local)  # before any pinned allocation: observation copies stay on the GPU's socket
 
     sc, cam, K, pose_sets = build_workload(rank)
     I = E_PER_GPU
@@ -308,6 +313,7 @@ def run_ours(args):
         }
         if gather:
             line["obs_gather"] = gather
+            line["cpu_affinity"] = f"rank 0 bound to the {len(numa_cpus)} CPUs NVML reports local to its GPU" if numa_cpus else "unchanged"
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sc, cam, K, pose_sets[0], envs=32, reps=3)
         print(json.dumps(line), flush=True)

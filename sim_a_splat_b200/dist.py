@@ -54,3 +54,29 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"))
     return rank, world, local
+
+
+def bind_to_gpu_numa(device: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs NVML reports as local to `device` (its NUMA node), before any pinned host memory
+    is allocated: with one process per GPU the observation copies (16.5 MB per step and GPU in BASELINE configs[1])
+    then stay on the socket the GPU hangs off instead of crossing the inter-socket link.  Returns the CPU list, or
+    None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
