@@ -296,6 +296,24 @@ def test_pipelined_renderer_two_steps_in_flight_matches_blocking():
         pr.close()
 
 
+def test_compositor_without_contributor_count_gives_the_same_images():
+    """The compositor instance that does not count contributors (chosen when n_contrib is not requested -- what
+    bench.py runs) must produce the images of the counting instance bit for bit."""
+    sc = S.make_synthetic_scene(25000, 3, seed=41, link_counts=(1200, 700, 300))
+    W, H, E = 160, 112, 3
+    vms = np.repeat(S.ring_cameras(1, (0, 0, 0), seed=7), E, axis=0)
+    r = SplatRenderer(sc, max_images=E, max_envs=E, max_width=W, max_height=H)
+    r.set_link_poses(S.random_link_poses(E, 3, seed=70))
+    r.set_cameras(vms, S.fov_intrinsics(W, H), W, H, np.arange(E))
+    with_nc = {k: v.clone() for k, v in r.render(("rgb", "depth", "alpha", "rgb_u8", "n_contrib"), background=(0.2, 0.4, 0.6)).items()}
+    assert int(with_nc["n_contrib"].max()) > 0
+    for _ in range(2):  # direct launch, then the graph replay
+        without = r.render(("rgb", "depth", "alpha", "rgb_u8"), background=(0.2, 0.4, 0.6))
+        for k in ("rgb", "depth", "alpha", "rgb_u8"):
+            assert torch.equal(without[k], with_nc[k]), k
+    r.close()
+
+
 def test_overflow_is_reported_and_regrown():
     sc = S.make_synthetic_scene(30000, 1, seed=17)
     W, H = 128, 128
