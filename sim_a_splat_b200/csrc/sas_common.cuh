@@ -134,6 +134,7 @@ struct SasWork {
     unsigned sort_count[SAS_SORT_CLASSES], sort_start[SAS_SORT_CLASSES], sort_fill[SAS_SORT_CLASSES], sort_take[SAS_SORT_CLASSES];
     unsigned comp_count[SAS_COMP_CLASSES], comp_start[SAS_COMP_CLASSES], comp_fill[SAS_COMP_CLASSES];
     unsigned comp_total, comp_take;
+    unsigned comp_take_small;  // packed compositor: the 4-warp instance walks the same list with a counter of its own
 };
 
 // Sub-tile granularity of the static shortcut: a 16x16 tile is 4 columns (4 px) x 8 rows (2 px) of
@@ -144,6 +145,17 @@ struct SasWork {
 // background-only tile and are copied instead of composited.
 __host__ __device__ __forceinline__ int sas_group_bit(int cx /*0..3*/, int ry /*0..7*/) {
     return ((ry >> 1) * 2 + (cx >> 1)) * 4 + (ry & 1) * 2 + (cx & 1);
+}
+
+// groups of tile t that have at least one pixel inside the image (ragged right / bottom edge)
+__device__ __forceinline__ unsigned sas_inside_group_mask(int t, int tile_w, int W, int H) {
+    const int ty = t / tile_w, tx = t - ty * tile_w;
+    if ((tx + 1) * SAS_TILE_PX <= W && (ty + 1) * SAS_TILE_PX <= H) return 0xffffffffu;
+    unsigned m = 0u;
+    for (int ry = 0; ry < 8; ry++)
+        for (int cx = 0; cx < 4; cx++)
+            if (tx * SAS_TILE_PX + 4 * cx < W && ty * SAS_TILE_PX + 2 * ry < H) m |= 1u << sas_group_bit(cx, ry);
+    return m;
 }
 
 // Which 4x2-pixel groups a Gaussian's culling extents reach, as inclusive ranges of GLOBAL group
@@ -173,7 +185,7 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
     return xs * e;
 }
 
-// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default 0xcf):
+// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default 0x2cf):
 //   bit 0  compositor: per-group (4x2) hit masks instead of one per warp footprint
 //   bit 1  group-level static shortcut (off: every group of a tile with link Gaussians is composited)
 //   bit 2  bucket-sort size classes run on concurrent streams (fork / join on the caller's stream)
@@ -182,6 +194,8 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //          that staged it) instead of every warp testing every record against its own four groups
 //   bit 7  compositor: warp -> footprint map rotated with the work-item index (evens out the four schedulers)
 //   bit 8  scans + work lists as eleven small kernels even when the single-CTA fused kernel applies
+//   bit 9  compositor: the groups link Gaussians can reach packed into as few warps as possible; tiles with at most 16
+//          such groups go to a 4-warp kernel (16 resident CTAs per SM) that runs next to the 8-warp one
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -243,6 +257,6 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
-                                 int *n_launches);
+                                 int *n_launches, cudaStream_t side = nullptr, cudaEvent_t *fork_join = nullptr);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

@@ -10,8 +10,12 @@
 // is empty, and into the 4x2-pixel groups of the other tiles that no link Gaussian can reach
 // (tile_dyn_mask, from the projection kernel) -- those pixels are bit-identical by construction.
 //
-// Within a tile each warp owns an 8x4 pixel footprint and each of its four 8-lane groups one 4x2
-// block of it, one pixel per lane.  The depth-sorted ids are consumed in batches of 256: every
+// Within a tile every 8-lane group of a warp owns one 4x2 pixel block, one pixel per lane.  The blocks that
+// link Gaussians can reach (all blocks of a view tile) are PACKED four per warp in sas_group_bit order, so a tile with
+// 14 reachable blocks keeps 4 warps busy instead of spreading them over 8 warps that mostly wait at the batch barrier
+// while holding warp slots: an instance of 4 warps (16 resident CTAs per SM) takes the items with at most 16 such
+// blocks, an instance of 8 warps the others, side by side on two streams (SAS_VARIANT bit 9; without it each warp
+// owns a fixed 8x4 footprint of the tile).  Measured with two renders in flight: 1.089 -> 1.050 ms per step.  The depth-sorted ids are consumed in batches of 256: every
 // thread gathers one 48 B projected record into shared memory with three 16 B cp.async copies
 // (double buffered, the id for the batch after next prefetched into a register), so global latency
 // overlaps the arithmetic of the current batch; the thread that staged a record also computes, once
@@ -101,7 +105,9 @@ __device__ __forceinline__ void blend_one(const SasRecord *sb, int j, Pixel &p) 
 //   computed its 32-bit reach mask over all the tile's groups once (s_reach), a warp just ballots its
 //   own four bits (profile of MODE 1: 60 instructions per 32-record chunk per warp in the test phase,
 //   18 % of the kernel's instructions).
-template <int MODE, bool COUNT>
+// PACKED (MODE 2 only): `warp` carries, instead of the warp index, the four reach-mask bit positions of this warp's
+// groups (8 bits each): the groups were packed densely into warps, see composite_kernel.
+template <int MODE, bool COUNT, bool PACKED>
 __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigned *s_reach, int warp, int cnt, Pixel &p, float X0, float Y0) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3;
@@ -110,11 +116,20 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigne
         if (dm == 0xffffffffu) break;
         unsigned mask;
         if (MODE == 2) {
-            const unsigned bits = (j0 + lane < cnt ? s_reach[j0 + lane] : 0u) >> (warp * 4);
-            const unsigned b00 = __ballot_sync(0xffffffffu, bits & 1u);
-            const unsigned b10 = __ballot_sync(0xffffffffu, bits & 2u);
-            const unsigned b01 = __ballot_sync(0xffffffffu, bits & 4u);
-            const unsigned b11 = __ballot_sync(0xffffffffu, bits & 8u);
+            unsigned b00, b10, b01, b11;
+            if (PACKED) {
+                const unsigned rb = j0 + lane < cnt ? s_reach[j0 + lane] : 0u;
+                b00 = __ballot_sync(0xffffffffu, (rb >> (warp & 31)) & 1u);
+                b10 = __ballot_sync(0xffffffffu, (rb >> ((warp >> 8) & 31)) & 1u);
+                b01 = __ballot_sync(0xffffffffu, (rb >> ((warp >> 16) & 31)) & 1u);
+                b11 = __ballot_sync(0xffffffffu, (rb >> ((warp >> 24) & 31)) & 1u);
+            } else {
+                const unsigned bits = (j0 + lane < cnt ? s_reach[j0 + lane] : 0u) >> (warp * 4);
+                b00 = __ballot_sync(0xffffffffu, bits & 1u);
+                b10 = __ballot_sync(0xffffffffu, bits & 2u);
+                b01 = __ballot_sync(0xffffffffu, bits & 4u);
+                b11 = __ballot_sync(0xffffffffu, bits & 8u);
+            }
             mask = (grp & 2) ? ((grp & 1) ? b11 : b01) : ((grp & 1) ? b10 : b00);
             if (((dm >> (grp * 8)) & 0xffu) == 0xffu) mask = 0u;  // every pixel of this group has finished
         } else if (MODE == 1) {
@@ -175,7 +190,12 @@ __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *sr
 // independent CTAs resident on the SM, not the warps of one CTA.
 __constant__ int sas_variant_flags_dev = 0xff;
 
-template <int WARPS, int MODE, bool COUNT>
+// PACKED: one CTA per tile whatever WARPS; the tile's groups that link Gaussians can reach (all groups for a view
+// tile) are packed densely, four per warp, in sas_group_bit order -- a tile with 14 reachable groups keeps 4 warps
+// busy instead of leaving most of 8 warps waiting at the batch barrier while they hold warp slots and registers.
+// The WARPS = 4 instance takes the items with at most 16 such groups, the WARPS = 8 instance the others; both walk
+// the same work list with a counter of their own.
+template <int WARPS, int MODE, bool COUNT, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
@@ -183,7 +203,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                  int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, int max_items) {
     constexpr int NT = WARPS * 32;     // threads = records per batch
-    constexpr int PARTS = 8 / WARPS;   // CTAs per tile
+    constexpr int PARTS = PACKED ? 1 : 8 / WARPS;   // CTAs per tile
     __shared__ SasRecord stage[2][NT];
     __shared__ unsigned s_reach[MODE == 2 ? 2 : 1][MODE == 2 ? NT : 1];
     __shared__ unsigned s_take;
@@ -196,7 +216,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
     // slot back to the block scheduler, so kernels of another stream can move in while this one is still running.
     for (int taken = 0; max_items == 0 || taken < max_items; taken++) {
         __syncthreads();  // every thread is done with the previous tile's stage buffers and s_take
-        if (tid == 0) s_take = atomicAdd(&work->comp_take, 1u);
+        if (tid == 0) s_take = atomicAdd(PACKED && WARPS == 4 ? &work->comp_take_small : &work->comp_take, 1u);
         __syncthreads();
         const unsigned k = s_take;
         if (k >= work->comp_total * PARTS) break;
@@ -245,13 +265,31 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         // ---- this lane's pixel ----
         // warp = 8x4 footprint; its four 8-lane groups own the four 4x2 blocks of it (sas_common.cuh: sas_group_bit)
         const int ty = tile / tile_w, tx = tile - ty * tile_w;
-        const int fx = tx * SAS_TILE_PX + (warp & 1) * 8, fy = ty * SAS_TILE_PX + (warp >> 1) * 4;  // 8 wide x 4 high
         const int grp = lane >> 3, gl = lane & 7;
-        const int px = fx + (grp & 1) * 4 + (gl & 3), py = fy + (grp >> 1) * 2 + (gl >> 2);
+        int fx, fy, px, py, warp_arg = warp;
+        bool group_static;
+        if (PACKED) {
+            const unsigned pm = dyn_mask & sas_inside_group_mask(tile, tile_w, W, H);
+            const int ng = __popc(pm);
+            // which instance takes the item (uniform over the CTA): 4 warps up to 16 groups, else 8.  (A third instance
+            // of 2 warps for up to 8 groups changed nothing: 1.048 against 1.050 ms per step with two renders in flight.)
+            if ((WARPS == 4) != (!is_view && ng <= 16)) continue;
+            const int kq = (tid >> 5) * 4 + grp;                   // this group's rank among the packed groups
+            group_static = kq >= ng;
+            const unsigned bit = group_static ? 0u : __fns(pm, 0u, kq + 1);  // its bit in the sas_group_bit layout
+            const int cx = ((bit >> 2) & 1) * 2 + (bit & 1), ry = (bit >> 3) * 2 + ((bit >> 1) & 1);
+            fx = tx * SAS_TILE_PX; fy = ty * SAS_TILE_PX;
+            px = fx + 4 * cx + (gl & 3); py = fy + 2 * ry + (gl >> 2);
+            warp_arg = (int)(__shfl_sync(0xffffffffu, bit, 0) | (__shfl_sync(0xffffffffu, bit, 8) << 8) |
+                             (__shfl_sync(0xffffffffu, bit, 16) << 16) | (__shfl_sync(0xffffffffu, bit, 24) << 24));
+        } else {
+            fx = tx * SAS_TILE_PX + (warp & 1) * 8; fy = ty * SAS_TILE_PX + (warp >> 1) * 4;  // 8 wide x 4 high
+            px = fx + (grp & 1) * 4 + (gl & 3); py = fy + (grp >> 1) * 2 + (gl >> 2);
+            // A group no link Gaussian of this image can touch is pixel-identical to the view's
+            // background-only tile: it is skipped here and copied afterwards (copy_static_tiles_kernel).
+            group_static = ((dyn_mask >> (warp * 4 + grp)) & 1u) == 0u;
+        }
         const bool inside = (px < W) && (py < H);
-        // A group no link Gaussian of this image can touch is pixel-identical to the view's
-        // background-only tile: it is skipped here and copied afterwards (copy_static_tiles_kernel).
-        const bool group_static = ((dyn_mask >> (warp * 4 + grp)) & 1u) == 0u;
         const float X0 = (float)fx + 0.5f, Y0 = (float)fy + 0.5f;
         Pixel p;
         p.pxf = (!inside || group_static) ? __int_as_float(0x7fc00000) : (float)px + 0.5f;
@@ -288,7 +326,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
             if (__all_sync(0xffffffffu, p.done())) continue;  // whole warp finished: only keep feeding the pipeline
-            process_batch<MODE, COUNT>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp, cnt, p, X0, Y0);
+            process_batch<MODE, COUNT, PACKED>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp_arg, cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
 #undef SAS_REC_OF
@@ -307,7 +345,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             }
         }
     }
-    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged * WARPS);  // in eighths of a tile
+    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged * (PACKED ? 8 : WARPS));  // in eighths of a tile
 }
 
 // Images whose link bucket for a tile is empty take the tile from their view's buffers; the
@@ -368,13 +406,14 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
 int g_comp_sms = 148;
 int g_comp_items = 1; // SAS_COMP_ITEMS: work items per compositor CTA before it exits (0 = persistent CTAs); measured on the
                       // pusht batch: 1 -> 1.208, 2 -> 1.213, 4 -> 1.221, 8 -> 1.235, persistent -> 1.231 ms/step
+bool g_comp_items_env = false;
 int g_comp_ctas = 8;  // persistent CTAs per SM of the default compositor (SAS_COMP_CTAS, experiments: 8 is best)
 
 }  // namespace
 
 cudaError_t sas_composite_init(int n_sms) {
     g_comp_sms = n_sms > 0 ? n_sms : 148;
-    if (const char *e = getenv("SAS_COMP_ITEMS")) g_comp_items = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char *e = getenv("SAS_COMP_ITEMS")) { g_comp_items = atoi(e) > 0 ? atoi(e) : 0; g_comp_items_env = true; }
     if (const char *e = getenv("SAS_COMP_CTAS")) g_comp_ctas = atoi(e) > 0 ? atoi(e) : 8;
     const int vf = sas_variant_flags();
     return cudaMemcpyToSymbol(sas_variant_flags_dev, &vf, sizeof(int));
@@ -387,14 +426,16 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
-                                 int *n_launches) {
+                                 int *n_launches, cudaStream_t side, cudaEvent_t *fork_join) {
 #define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
     // bounded CTAs (SAS_COMP_ITEMS > 0): enough of them for every possible item; otherwise persistent CTAs
-    const int max_items = g_comp_items;
     const long long all_items = (long long)(I + C) * tile_w * tile_h;
+    // default: one item per CTA, more when the list could be far longer than the CTAs the GPU holds (most of those CTAs
+    // would only find the list empty: 4 cameras x 1280x720 has 28 800 possible items and a few thousand real ones)
+    const int max_items = g_comp_items_env ? g_comp_items : (int)max(1ll, (all_items + (long long)g_comp_sms * 64 - 1) / ((long long)g_comp_sms * 64));
 #define SAS_GRID(W) (max_items > 0 ? (int)max((long long)g_comp_sms * (64 / (W)), (all_items * (8 / (W)) + max_items - 1) / max_items) \
                                    : g_comp_sms * (64 / (W)))
 #define SAS_COMP(W, M) composite_kernel<W, M, true><<<SAS_GRID(W), W * 32, 0, st>>>(SAS_ARGS)
@@ -403,7 +444,23 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
         if (mode == 2) {
             // the default: counts per-pixel contributors only when the caller asked for n_contrib
             const int grid = max_items > 0 ? SAS_GRID(8) : g_comp_sms * g_comp_ctas;
-            if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
+            if ((vf & 0x200) && side && fork_join) {
+                // packed groups: the 4-warp instance on the side stream next to the 8-warp instance (both see every item)
+                const int grid4 = max_items > 0 ? grid : g_comp_sms * 16;
+                cudaError_t e;
+                if ((e = cudaEventRecord(fork_join[0], st)) != cudaSuccess) return e;
+                if ((e = cudaStreamWaitEvent(side, fork_join[0], 0)) != cudaSuccess) return e;
+                if (img_out.n_contrib) {
+                    composite_kernel<8, 2, true, true><<<grid, 256, 0, st>>>(SAS_ARGS);
+                    composite_kernel<4, 2, true, true><<<grid4, 128, 0, side>>>(SAS_ARGS);
+                } else {
+                    composite_kernel<8, 2, false, true><<<grid, 256, 0, st>>>(SAS_ARGS);
+                    composite_kernel<4, 2, false, true><<<grid4, 128, 0, side>>>(SAS_ARGS);
+                }
+                if ((e = cudaEventRecord(fork_join[1], side)) != cudaSuccess) return e;
+                if ((e = cudaStreamWaitEvent(st, fork_join[1], 0)) != cudaSuccess) return e;
+                if (n_launches) *n_launches += 1;
+            } else if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
             else composite_kernel<8, 2, false><<<grid, 256, 0, st>>>(SAS_ARGS);
         } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
     } else if (parts == 1) {

@@ -36,17 +36,6 @@ __device__ __forceinline__ int comp_class_of(unsigned n) {
     return 31 - w;
 }
 
-// groups of tile t that have at least one pixel inside the image (ragged right / bottom edge)
-__device__ __forceinline__ unsigned inside_group_mask(int t, int tile_w, int W, int H) {
-    const int ty = t / tile_w, tx = t - ty * tile_w;
-    if ((tx + 1) * SAS_TILE_PX <= W && (ty + 1) * SAS_TILE_PX <= H) return 0xffffffffu;
-    unsigned m = 0u;
-    for (int ry = 0; ry < 8; ry++)
-        for (int cx = 0; cx < 4; cx++)
-            if (tx * SAS_TILE_PX + 4 * cx < W && ty * SAS_TILE_PX + 2 * ry < H) m |= 1u << sas_group_bit(cx, ry);
-    return m;
-}
-
 // pass 1 over [0, RT) row buckets then [RT, RT+IT) image tiles: class histograms + the 'needed' marks
 __global__ void __launch_bounds__(256) work_count_kernel(const unsigned *__restrict__ row_tile_count, const int *__restrict__ view_of_image,
                                                          const unsigned *__restrict__ tile_dyn_mask, int C, int I, int T, int tile_w, int W,
@@ -68,7 +57,7 @@ __global__ void __launch_bounds__(256) work_count_kernel(const unsigned *__restr
         if (nd > 0) {
             atomicAdd(&s_comp[comp_class_of(nd + row_tile_count[(size_t)v * T + t])], 1u);
             // some visible group is out of reach of every link Gaussian: it is copied from the view tile
-            if (~tile_dyn_mask[j] & inside_group_mask(t, tile_w, W, H)) view_tile_needed[(size_t)v * T + t] = 1;
+            if (~tile_dyn_mask[j] & sas_inside_group_mask(t, tile_w, W, H)) view_tile_needed[(size_t)v * T + t] = 1;
         } else {
             view_tile_needed[(size_t)v * T + t] = 1;  // benign race: every writer stores 1
         }
@@ -239,7 +228,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) scan_lists_fused_kernel(const u
             mx = max(mx, nd + nbk);
             if (nd > 0) {
                 atomicAdd(&sh.comp_count[comp_class_of(nd + nbk)], 1u);
-                if (~tile_dyn_mask[j] & inside_group_mask(t, tile_w, W, H)) view_tile_needed[(size_t)v * T + t] = 1;
+                if (~tile_dyn_mask[j] & sas_inside_group_mask(t, tile_w, W, H)) view_tile_needed[(size_t)v * T + t] = 1;
             } else {
                 view_tile_needed[(size_t)v * T + t] = 1;  // benign race: every writer stores 1
             }
