@@ -336,8 +336,9 @@ class PipelinedSplatRenderer:
     its own work; the images are bit-identical to SplatRenderer's (tests/test_gpu_parity.py).
 
     Use: set_cameras once; per step set_link_poses(...) (or set_link_poses_from_bodies) then render_async() -> ticket;
-    wait(ticket) returns that step's pinned host tensors.  Keep at most `depth` steps outstanding: issue step k+1,
-    then wait for step k.  The tensors of step k are reused by step k + 2*depth.
+    wait(ticket) returns that step's pinned host tensors.  Up to 2*depth steps may be outstanding (every handle
+    double-buffers its staging and host buffers): issuing step k and then waiting for step k-depth keeps every handle's
+    next render queued behind its current one.  The tensors of step k are reused by step k + 2*depth.
 
     The reference has no counterpart (it blocks on one browser round trip per camera,
     /root/reference/sim_a_splat/env/splat/splat_env_wrapper.py:147-158); this is the step_async / step_wait split of
