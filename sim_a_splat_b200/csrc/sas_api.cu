@@ -53,7 +53,6 @@ struct sas_renderer {
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     cudaEvent_t scan_ev[3] = {};                      // fork / two joins of the scan + work-list chains
     cudaEvent_t span_ev[2] = {};                      // fork / join of the background span next to the link span
-    cudaEvent_t comp_ev[2] = {};                      // fork / join of the 4-warp packed compositor next to the 8-warp one
     // device staging when the caller's outputs are host memory; set [1] only for SAS_MEM_HOST_ASYNC, which alternates
     // between the two so that the D2H copy of one render overlaps the next render
     DevBuf o_rgb[2], o_depth[2], o_alpha[2], o_u8[2], o_nc[2];
@@ -260,7 +259,6 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     for (cudaEvent_t &ev : r->fork_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (cudaEvent_t &ev : r->scan_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (cudaEvent_t &ev : r->span_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (cudaEvent_t &ev : r->comp_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
     long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
@@ -287,8 +285,6 @@ void sas_destroy(sas_renderer *r) {
     for (cudaEvent_t ev : r->scan_ev)
         if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : r->span_ev)
-        if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : r->comp_ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &g : r->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -574,7 +570,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     const SasViewBuf view_out{(float *)r->v_acc.p, (float *)r->v_depth.p, (int *)r->v_nc.p};
     SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, dyn_mask, (const int *)r->comp_list.p, work,
                                      r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, r->max_isects, r->max_isects,
-                                     r->counters, st, &launches, r->aux[0], r->comp_ev));
+                                     r->counters, st, &launches));
     SAS_STAGE(5);
     if (ns) {
         SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, I, W, H, out->background[0], out->background[1],

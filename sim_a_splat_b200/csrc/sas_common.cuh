@@ -134,7 +134,6 @@ struct SasWork {
     unsigned sort_count[SAS_SORT_CLASSES], sort_start[SAS_SORT_CLASSES], sort_fill[SAS_SORT_CLASSES], sort_take[SAS_SORT_CLASSES];
     unsigned comp_count[SAS_COMP_CLASSES], comp_start[SAS_COMP_CLASSES], comp_fill[SAS_COMP_CLASSES];
     unsigned comp_total, comp_take;
-    unsigned comp_take_small;  // packed compositor: the 4-warp instance walks the same list with a counter of its own
 };
 
 // Sub-tile granularity of the static shortcut: a 16x16 tile is 4 columns (4 px) x 8 rows (2 px) of
@@ -194,8 +193,7 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //          that staged it) instead of every warp testing every record against its own four groups
 //   bit 7  compositor: warp -> footprint map rotated with the work-item index (evens out the four schedulers)
 //   bit 8  scans + work lists as eleven small kernels even when the single-CTA fused kernel applies
-//   bit 9  compositor: the groups link Gaussians can reach packed into as few warps as possible; tiles with at most 16
-//          such groups go to a 4-warp kernel (16 resident CTAs per SM) that runs next to the 8-warp one
+//   bit 9  compositor: the groups link Gaussians can reach packed four per warp, a tile = one or two CTAs of 4 warps
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -257,6 +255,6 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
-                                 int *n_launches, cudaStream_t side = nullptr, cudaEvent_t *fork_join = nullptr);
+                                 int *n_launches);
 cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
                                float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

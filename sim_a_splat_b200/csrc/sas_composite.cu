@@ -10,12 +10,15 @@
 // is empty, and into the 4x2-pixel groups of the other tiles that no link Gaussian can reach
 // (tile_dyn_mask, from the projection kernel) -- those pixels are bit-identical by construction.
 //
-// Within a tile every 8-lane group of a warp owns one 4x2 pixel block, one pixel per lane.  The blocks that
-// link Gaussians can reach (all blocks of a view tile) are PACKED four per warp in sas_group_bit order, so a tile with
-// 14 reachable blocks keeps 4 warps busy instead of spreading them over 8 warps that mostly wait at the batch barrier
-// while holding warp slots: an instance of 4 warps (16 resident CTAs per SM) takes the items with at most 16 such
-// blocks, an instance of 8 warps the others, side by side on two streams (SAS_VARIANT bit 9; without it each warp
-// owns a fixed 8x4 footprint of the tile).  Measured with two renders in flight: 1.089 -> 1.050 ms per step.  The depth-sorted ids are consumed in batches of 256: every
+// Within a tile every 8-lane group of a warp owns one 4x2 pixel block, one pixel per lane.  The blocks that link
+// Gaussians can reach (all blocks of a view tile) are PACKED four per warp in sas_group_bit order and the tile is
+// composited by one CTA of 4 warps (up to 16 such blocks) or two (more), each staging the list for itself: warps that
+// would mostly wait at the batch barrier no longer hold warp slots, and there is one CTA shape (16 resident per SM).
+// (SAS_VARIANT bit 9; without it a tile is one CTA of 8 warps, each owning a fixed 8x4 footprint.)  Measured:
+// 1.207 -> 1.144 ms per step alone, 1.089 -> 1.010 ms with two renders in flight.  (Tried on the way: a 4-warp
+// instance for tiles of <= 16 blocks next to an 8-warp instance for the rest, 1.202 / 1.050; plus a 6-warp instance,
+// 1.314 / 1.084; CTAs of 2 warps and up to four per tile, 1.195 / 1.070.)
+// The depth-sorted ids are consumed in batches of 256: every
 // thread gathers one 48 B projected record into shared memory with three 16 B cp.async copies
 // (double buffered, the id for the batch after next prefetched into a register), so global latency
 // overlaps the arithmetic of the current batch; the thread that staged a record also computes, once
@@ -190,11 +193,10 @@ __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *sr
 // independent CTAs resident on the SM, not the warps of one CTA.
 __constant__ int sas_variant_flags_dev = 0xff;
 
-// PACKED: one CTA per tile whatever WARPS; the tile's groups that link Gaussians can reach (all groups for a view
-// tile) are packed densely, four per warp, in sas_group_bit order -- a tile with 14 reachable groups keeps 4 warps
-// busy instead of leaving most of 8 warps waiting at the batch barrier while they hold warp slots and registers.
-// The WARPS = 4 instance takes the items with at most 16 such groups, the WARPS = 8 instance the others; both walk
-// the same work list with a counter of their own.
+// PACKED (WARPS = 4): the tile's groups that link Gaussians can reach (all groups for a view tile) are packed densely,
+// four per warp, in sas_group_bit order, and the tile becomes ONE CTA of 4 warps (up to 16 packed groups) or TWO (more
+// than 16): a tile with 14 reachable groups keeps 4 warps busy instead of leaving most of 8 warps waiting at the
+// batch barrier while they hold warp slots and registers.  One CTA shape, 16 resident per SM.
 template <int WARPS, int MODE, bool COUNT, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
@@ -203,20 +205,20 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                  int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, int max_items) {
     constexpr int NT = WARPS * 32;     // threads = records per batch
-    constexpr int PARTS = PACKED ? 1 : 8 / WARPS;   // CTAs per tile
+    constexpr int PARTS = 8 / WARPS;   // CTAs per tile (PACKED: at most; a part beyond the tile's packed groups is skipped)
     __shared__ SasRecord stage[2][NT];
     __shared__ unsigned s_reach[MODE == 2 ? 2 : 1][MODE == 2 ? NT : 1];
     __shared__ unsigned s_take;
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = tile_w * tile_h;
     const long long IT = (long long)I * T;
-    int staged = 0;
+    unsigned staged = 0;   // in eighths of a tile's list: a list staged by the two CTAs of a tile counts once
 
     // max_items: work items a CTA takes before it exits (0 = until the list is empty).  A bounded CTA hands its SM
     // slot back to the block scheduler, so kernels of another stream can move in while this one is still running.
     for (int taken = 0; max_items == 0 || taken < max_items; taken++) {
         __syncthreads();  // every thread is done with the previous tile's stage buffers and s_take
-        if (tid == 0) s_take = atomicAdd(PACKED && WARPS == 4 ? &work->comp_take_small : &work->comp_take, 1u);
+        if (tid == 0) s_take = atomicAdd(&work->comp_take, 1u);
         __syncthreads();
         const unsigned k = s_take;
         if (k >= work->comp_total * PARTS) break;
@@ -268,13 +270,16 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         const int grp = lane >> 3, gl = lane & 7;
         int fx, fy, px, py, warp_arg = warp;
         bool group_static;
+        int stage_weight = WARPS;
         if (PACKED) {
             const unsigned pm = dyn_mask & sas_inside_group_mask(tile, tile_w, W, H);
             const int ng = __popc(pm);
-            // which instance takes the item (uniform over the CTA): 4 warps up to 16 groups, else 8.  (A third instance
-            // of 2 warps for up to 8 groups changed nothing: 1.048 against 1.050 ms per step with two renders in flight.)
-            if ((WARPS == 4) != (!is_view && ng <= 16)) continue;
-            const int kq = (tid >> 5) * 4 + grp;                   // this group's rank among the packed groups
+            // part p of the tile holds packed groups [p * WARPS * 4, (p + 1) * WARPS * 4); a part past the last group has
+            // nothing to do (uniform over the CTA)
+            const int part = (int)(k % PARTS);
+            if (part > 0 && part * WARPS * 4 >= ng) continue;
+            if (ng <= WARPS * 4) stage_weight = 8;                     // the only CTA of this tile
+            const int kq = part * WARPS * 4 + (tid >> 5) * 4 + grp;   // this group's rank among the packed groups
             group_static = kq >= ng;
             const unsigned bit = group_static ? 0u : __fns(pm, 0u, kq + 1);  // its bit in the sas_group_bit layout
             const int cx = ((bit >> 2) & 1) * 2 + (bit & 1), ry = (bit >> 3) * 2 + ((bit >> 1) & 1);
@@ -316,7 +321,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             }
             if (__syncthreads_count(p.done()) == NT) break;  // also publishes batch b (records and reach masks) to the CTA
             const int cnt = min(NT, n - b * NT);
-            staged += cnt;
+            staged += (unsigned)(cnt * stage_weight);
             const int buf = b & 1;
             {  // batch b+1 -> other buffer; id of batch b+2 -> register
                 const int e1 = (b + 1) * NT + tid;
@@ -345,7 +350,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             }
         }
     }
-    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged * (PACKED ? 8 : WARPS));  // in eighths of a tile
+    if (tid == 0 && staged) atomicAdd(&counters->n_staged, (unsigned long long)staged);
 }
 
 // Images whose link bucket for a tile is empty take the tile from their view's buffers; the
@@ -426,7 +431,7 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  const unsigned int *tile_dyn_mask, const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
-                                 int *n_launches, cudaStream_t side, cudaEvent_t *fork_join) {
+                                 int *n_launches) {
 #define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
@@ -444,22 +449,10 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
         if (mode == 2) {
             // the default: counts per-pixel contributors only when the caller asked for n_contrib
             const int grid = max_items > 0 ? SAS_GRID(8) : g_comp_sms * g_comp_ctas;
-            if ((vf & 0x200) && side && fork_join) {
-                // packed groups: the 4-warp instance on the side stream next to the 8-warp instance (both see every item)
-                const int grid4 = max_items > 0 ? grid : g_comp_sms * 16;
-                cudaError_t e;
-                if ((e = cudaEventRecord(fork_join[0], st)) != cudaSuccess) return e;
-                if ((e = cudaStreamWaitEvent(side, fork_join[0], 0)) != cudaSuccess) return e;
-                if (img_out.n_contrib) {
-                    composite_kernel<8, 2, true, true><<<grid, 256, 0, st>>>(SAS_ARGS);
-                    composite_kernel<4, 2, true, true><<<grid4, 128, 0, side>>>(SAS_ARGS);
-                } else {
-                    composite_kernel<8, 2, false, true><<<grid, 256, 0, st>>>(SAS_ARGS);
-                    composite_kernel<4, 2, false, true><<<grid4, 128, 0, side>>>(SAS_ARGS);
-                }
-                if ((e = cudaEventRecord(fork_join[1], side)) != cudaSuccess) return e;
-                if ((e = cudaStreamWaitEvent(st, fork_join[1], 0)) != cudaSuccess) return e;
-                if (n_launches) *n_launches += 1;
+            if (vf & 0x200) {  // packed groups: every tile as one or two 4-warp CTAs of up to 16 packed groups each
+                const int grid4 = max_items > 0 ? SAS_GRID(4) : g_comp_sms * 16;
+                if (img_out.n_contrib) composite_kernel<4, 2, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                else composite_kernel<4, 2, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
             } else if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
             else composite_kernel<8, 2, false><<<grid, 256, 0, st>>>(SAS_ARGS);
         } else if (mode == 1) SAS_COMP(8, 1); else SAS_COMP(8, 0);
