@@ -46,9 +46,23 @@ class VecSplatRenderer:
         self._fixed_vm = [c2w_opencv_to_viewmat(v["local_frame"].rotation().wxyz, v["local_frame"].translation()) for v in self.fixed.values()]
         self._static_cameras_set = False
 
-    def _set_step_inputs(self, draw_msgs: Sequence) -> None:
-        assert len(draw_msgs) == self.E
+    def _set_step_inputs(self, draw_msgs) -> None:
+        """draw_msgs: E draw messages (manipulator_env.py:377-390) -- or, for fixed cameras only, the body poses of all
+        envs at once as an [E,L,7] fp64 array / CUDA tensor (quaternion wxyz | position per link body, e.g. from
+        urdf_fk.BatchedBodyPoseSource.body_poses): no per-env Python on the step path."""
         r = self.renderer
+        if not isinstance(draw_msgs, (list, tuple)):
+            if self.moving:
+                raise ValueError("batched body poses carry no draw messages: link-attached cameras need render(draw_msgs)")
+            if r.L:
+                r.set_link_poses_from_bodies(draw_msgs)
+            if not self._static_cameras_set:
+                vms = self._fixed_vm * self.E
+                env = np.repeat(np.arange(self.E, dtype=np.int32), self.C)
+                r.set_cameras(np.stack(vms), self.K, self.W, self.H, env)
+                self._static_cameras_set = True
+            return
+        assert len(draw_msgs) == self.E
         if r.L:  # draw_handler's algebra runs on the device over all (env, link) at once (csrc/sas_pose.cu)
             r.set_link_poses_from_bodies(np.stack([self.handler.body_poses_from_msg(m) for m in draw_msgs]))  # [E,L,7] fp64
         if self.moving or not self._static_cameras_set:

@@ -154,6 +154,10 @@ def test_task_block_is_rendered_and_follows_its_pose(toy):
     out = vec.render(msgs)["camera_0"]
     for e in range(2):
         assert np.abs(out[e].astype(np.int32) - frames[e]).max() <= 1   # device fp64 composition vs host quaternion round trip
+    # the same step from pre-batched body poses [E,L,7] (no draw messages, no per-env Python): host array and CUDA tensor
+    bodies = np.stack([env.splat_handler.body_poses_from_msg(m) for m in msgs])
+    assert np.array_equal(vec.render(bodies)["camera_0"], out)
+    assert np.array_equal(vec.render(torch.from_numpy(bodies).cuda())["camera_0"], out)
     vec.close()
     env.close()
 
