@@ -561,7 +561,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, r->aux, r->fork_ev,
                                      &launches));
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects,
-                                 (sas_variant_flags() & 8) ? 0 : 1, st));
+                                 (sas_variant_flags() & 8) ? 0 : 1, (const int *)r->comp_list.p, work, st));
     launches += 1;
     SAS_STAGE(4);
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
@@ -775,7 +775,7 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
             // the render skips the id lists of tiles without link Gaussians (the compositor takes those from the
             // view's bucket); produce them now
             SAS_CUDA(r, sas_launch_merge((const uint2 *)r->pairs.p, (const int *)r->row_tile_offset.p, (const int *)r->img_tile_offset.p,
-                                         r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects, r->max_isects, 1, 0));
+                                         r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects, r->max_isects, 1, nullptr, nullptr, 0));
             SAS_CUDA(r, cudaDeviceSynchronize());
             src = r->merged.p; avail = (size_t)m * 4;
             break;

@@ -14,6 +14,8 @@
 // entry; merge reads 8 B per merged intersection and writes 4 B.
 #include "sas_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int SCAN_THREADS = 256;
@@ -238,11 +240,22 @@ __device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB ke
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                               const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
                                                               int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all,
-                                                              int fill_static) {
+                                                              int fill_static, const int *__restrict__ comp_list,
+                                                              const SasWork *__restrict__ work, int I) {
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
     __shared__ int s_out[MERGE_CHUNK];
     __shared__ int s_split[MERGE_MAX_SPLITS + 1];
-    const int t = blockIdx.x, i = blockIdx.y;
+    int t, i;
+    if (comp_list) {
+        // render path: CTA k takes entry k of the compositor's work list -- exactly the (image, tile) lists that need
+        // merging, longest first, so the 9 000-entry tiles start at once instead of finishing alone at the end
+        if (blockIdx.x >= work->comp_total) return;
+        const long long item = comp_list[blockIdx.x];
+        if (item >= (long long)I * T) return;  // a view tile: its bucket is composited as it is
+        i = (int)(item / T); t = (int)(item - (long long)i * T);
+    } else {
+        t = blockIdx.x; i = blockIdx.y;
+    }
     const size_t bb = (size_t)view_of_image[i] * T + t, db = (size_t)(C + i) * T + t;
     long long b0 = row_tile_offset[bb], b1 = row_tile_offset[bb + 1];
     long long d0 = row_tile_offset[db], d1 = row_tile_offset[db + 1];
@@ -328,9 +341,17 @@ cudaError_t sas_bin_init() {
 }
 
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
-                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static, cudaStream_t st) {
-    dim3 grid(T, I);
-    merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src, cap_all,
-                                                 fill_static);
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
+                             const int *comp_list, const SasWork *work, cudaStream_t st) {
+    static int lpt = -1;  // SAS_MERGE_LPT=0: one CTA per (tile, image) in grid order, as for debug fetches
+    if (lpt < 0) { const char *e = getenv("SAS_MERGE_LPT"); lpt = e ? atoi(e) : 1; }
+    if (comp_list && work && !fill_static && lpt) {
+        merge_kernel<<<(unsigned)((long long)(I + C) * T), MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T,
+                                                                                 merged_gid, cap_src, cap_all, 0, comp_list, work, I);
+    } else {
+        dim3 grid(T, I);
+        merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
+                                                     cap_all, fill_static, nullptr, nullptr, I);
+    }
     return cudaGetLastError();
 }

@@ -246,7 +246,8 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
                                  long long capacity, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
 // fill_static: also write the ids of tiles whose link bucket is empty (the compositor never reads those)
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
-                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static, cudaStream_t st);
+                             int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
+                             const int *comp_list, const SasWork *work, cudaStream_t st);
 cudaError_t sas_composite_init(int n_sms);
 // Composites the ordered work list (image tiles with link Gaussians + the needed view tiles), then
 // copies the view tiles into the images whose link bucket for that tile is empty.
