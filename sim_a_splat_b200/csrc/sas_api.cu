@@ -169,7 +169,7 @@ int sas_variant_flags() {
 
 extern "C" {
 
-const char *sas_version(void) { return "sas_b200 0.2.0 (sm_100a)"; }
+const char *sas_version(void) { return "sas_b200 0.3.0 (sm_100a)"; }
 
 const char *sas_last_error(const sas_renderer *r) { return r ? r->err.c_str() : g_create_error.c_str(); }
 
