@@ -49,6 +49,10 @@ def test_no_cpu_fallback_without_gpu():
     sc = S.make_synthetic_scene(64, 0, seed=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         SplatRenderer(sc)
+    from sim_a_splat_b200.renderer import PipelinedSplatRenderer
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PipelinedSplatRenderer(sc, depth=2)  # the two-steps-in-flight front end has no CPU path either
     # and straight through the C ABI
     lib = _lib.load()
     arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (sc.means, sc.quats, sc.scales, sc.opacities, sc.sh)]
@@ -59,6 +63,24 @@ def test_no_cpu_fallback_without_gpu():
     rc = lib.sas_create(C.byref(desc), C.byref(cfg), 0, C.byref(h))
     assert rc == -2 and not h.value  # SAS_ECUDA
     assert b"no CPU fallback" in lib.sas_last_error(None)
+
+
+def test_entry_points_reject_null_handles_without_touching_a_device():
+    lib = _lib.load()
+    assert lib.sas_wait_outputs(None, 0) == -1          # SAS_EINVAL
+    assert lib.sas_render(None, None, None) == -1
+    assert lib.sas_last_launch_count(None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_numa_binding_is_a_no_op_without_gpu():
+    import os
+
+    from sim_a_splat_b200.dist import bind_to_gpu_numa
+
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) is None
+    assert os.sched_getaffinity(0) == before
 
 
 def test_create_rejects_bad_arguments():
