@@ -74,7 +74,9 @@ typedef struct {
     int32_t max_envs;       /* E cap                                                  */
     int32_t max_width;      /* <= 4080 (tile coordinates are packed in 8 bits)        */
     int32_t max_height;
-    int64_t max_isects;     /* M cap (tile intersections per render call); 0 = auto   */
+    int64_t max_isects;     /* M cap: merged (image,tile,gaussian) intersections per render call; 0 = auto */
+    int64_t max_isects_src; /* cap of the bucket entries actually emitted and sorted (background once per VIEW +
+                               links per image; with shared cameras several times smaller than M); 0 = max_isects */
 } sas_config;
 
 /* Output buffers of one render call.  Any pointer may be NULL (not produced). */
@@ -97,7 +99,22 @@ typedef struct {
     uint8_t *rgb_u8;        /* [I,H,W,3] u8 = floor(clamp(rgb,0,1)*255+0.5): what
                                client.get_render returns (splat_env_wrapper.py:148-157) */
     int32_t *n_contrib;     /* [I,H,W]   Gaussians accumulated per pixel (diagnostic)  */
+    uint16_t *depth_f16;    /* [I,H,W]   IEEE binary16 bits of the expected depth (round to nearest even): 2 instead
+                               of 4 bytes per pixel for observation transfers (uint8 RGB + fp16 depth) */
 } sas_outputs;
+
+/* Host outputs travel in as few copies as possible: the library renders the requested outputs of a SAS_MEM_HOST /
+ * SAS_MEM_HOST_ASYNC call into ONE device staging block laid out as below, and when the caller's host pointers have
+ * the same relative layout (one pinned block cut up with sas_packed_layout) the whole observation goes out in a
+ * single cudaMemcpyAsync; otherwise one copy per output.  `want` is a mask of SAS_OUT_* bits; offsets[k] is the byte
+ * offset of output k (index = bit number; untouched when not wanted), every offset 256-byte aligned. */
+#define SAS_OUT_RGB_U8 1
+#define SAS_OUT_DEPTH_F16 2
+#define SAS_OUT_DEPTH 4
+#define SAS_OUT_ALPHA 8
+#define SAS_OUT_RGB 16
+#define SAS_OUT_NCONTRIB 32
+int sas_packed_layout(int n_images, int width, int height, int want, size_t offsets[6], size_t *total_bytes);
 
 /* Images that share a camera (bit-identical viewmat and K) share a VIEW: the background
  * (link_id < 0) is projected, binned and depth-sorted once per view, the link Gaussians once
@@ -112,6 +129,9 @@ typedef struct {
                                (sum over tiles, after early termination)               */
     int32_t overflow;       /* != 0 if an intersection count exceeded max_isects (frame is incomplete) */
     int32_t n_images, n_views, n_gaussians, n_background, width, height, tile_w, tile_h;
+    int32_t pad_;
+    int64_t cap_isects;     /* current capacities (sas_config.max_isects / max_isects_src, grown by sas_reserve_isects*) */
+    int64_t cap_isects_src;
 } sas_stats;
 
 /* Replaces: GSplatLoader -> SplatHandler._load_saved_splats + _add_robot_segmented_splats +
@@ -124,6 +144,11 @@ void sas_destroy(sas_renderer *r);
  * poses [n_envs, L, 12] fp32 = (rot row-major 3x3 | pos), meaning
  * mu' = rot*mu + pos, Sigma' = rot*Sigma*rot^T for every Gaussian of link l. */
 int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem, void *stream);
+/* Input lifetime (this call and sas_set_link_poses_from_bodies): the array is READ ASYNCHRONOUSLY by a copy enqueued
+ * on `stream`.  Host memory must stay valid and unchanged until that copy has run (pageable memory is staged by the
+ * driver before the call returns; pinned memory is not); device memory must not be overwritten by work on OTHER
+ * streams until an event recorded on `stream` after this call has completed -- the Python renderers take a private
+ * copy on the caller's stream first (SplatRenderer.set_link_poses), so their callers may reuse the tensor at once. */
 
 /* Replaces: the pose algebra of SplatHandler.draw_handler itself (splat_handler.py:250-281), run on the
  * device for all envs at once.  The model holds the constants of _load_saved_masks (:62-83: scale_factor,
@@ -176,6 +201,17 @@ int sas_wait_outputs(sas_renderer *r, int age);
 /* Grow the intersection buffers (pairs, sorted ids) to hold max_isects entries.  A render whose
  * intersection count exceeded the capacity sets sas_stats.overflow; reserve more and re-render. */
 int sas_reserve_isects(sas_renderer *r, long long max_isects);
+/* The same with separate capacities: max_src bucket entries (16 B each: pairs + their sort buffer), max_all merged
+ * ids (4 B each).  Either may be 0 = leave as it is. */
+int sas_reserve_isects2(sas_renderer *r, long long max_src, long long max_all);
+
+/* Overflow without a device synchronisation per frame.  The intersection counts stay on the device; every render
+ * leaves a snapshot of its counters in a small device ring.  Renders with host outputs bring their snapshot back
+ * with the observation: a SAS_MEM_HOST render, and sas_wait_outputs for a SAS_MEM_HOST_ASYNC one, return
+ * SAS_ECAPACITY when that frame was incomplete.  For device outputs, sas_poll_overflow reads the ring (it
+ * synchronises `stream`): returns 1 and the capacities that would have sufficed if any of the last (up to 4)
+ * renders since the previous poll / reserve overflowed, else 0; negative = error. */
+int sas_poll_overflow(sas_renderer *r, long long *need_src, long long *need_all, void *stream);
 
 /* Synchronises the device. */
 int sas_get_stats(sas_renderer *r, sas_stats *out);

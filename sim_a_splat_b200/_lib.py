@@ -27,7 +27,11 @@ EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
     "sas_set_pose_model", "sas_set_link_poses_from_bodies", "sas_unproject_depth", "sas_wait_outputs",
     "sas_get_stats", "sas_set_stage_timing", "sas_get_stage_ms", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
+    "sas_reserve_isects2", "sas_packed_layout", "sas_poll_overflow",
 ]
+
+# bit k of a SAS_OUT_* mask <-> output name (the order of sas_packed_layout)
+OUT_ORDER = ("rgb_u8", "depth_f16", "depth", "alpha", "rgb", "n_contrib")
 
 
 class SceneDesc(C.Structure):
@@ -38,20 +42,21 @@ class SceneDesc(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("max_images", C.c_int32), ("max_envs", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
-                ("max_isects", C.c_int64)]
+                ("max_isects", C.c_int64), ("max_isects_src", C.c_int64)]
 
 
 class Outputs(C.Structure):
     _fields_ = [("mem", C.c_int32), ("nerfstudio_post", C.c_int32), ("background", C.c_float * 3),
                 ("rgb", C.c_void_p), ("depth", C.c_void_p), ("alpha", C.c_void_p), ("rgb_u8", C.c_void_p),
-                ("n_contrib", C.c_void_p)]
+                ("n_contrib", C.c_void_p), ("depth_f16", C.c_void_p)]
 
 
 class Stats(C.Structure):
     _fields_ = [("n_isects", C.c_int64), ("n_isects_src", C.c_int64), ("n_visible_src", C.c_int64), ("max_tile_list", C.c_int64),
                 ("n_staged", C.c_int64), ("overflow", C.c_int32), ("n_images", C.c_int32), ("n_views", C.c_int32),
                 ("n_gaussians", C.c_int32), ("n_background", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
-                ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
+                ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("pad_", C.c_int32), ("cap_isects", C.c_int64),
+                ("cap_isects_src", C.c_int64)]
 
 
 class PoseModel(C.Structure):
@@ -103,6 +108,12 @@ def load(build_if_missing: bool = True):
     lib.sas_wait_outputs.restype = C.c_int
     lib.sas_reserve_isects.argtypes = [P, C.c_longlong]
     lib.sas_reserve_isects.restype = C.c_int
+    lib.sas_reserve_isects2.argtypes = [P, C.c_longlong, C.c_longlong]
+    lib.sas_reserve_isects2.restype = C.c_int
+    lib.sas_packed_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.sas_packed_layout.restype = C.c_int
+    lib.sas_poll_overflow.argtypes = [P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), P]
+    lib.sas_poll_overflow.restype = C.c_int
     lib.sas_get_stats.argtypes = [P, C.POINTER(Stats)]
     lib.sas_get_stats.restype = C.c_int
     lib.sas_set_stage_timing.argtypes = [P, C.c_int]

@@ -55,12 +55,22 @@ struct sas_renderer {
     cudaEvent_t span_ev[2] = {};                      // fork / join of the background span next to the link span
     // device staging when the caller's outputs are host memory; set [1] only for SAS_MEM_HOST_ASYNC, which alternates
     // between the two so that the D2H copy of one render overlaps the next render
-    DevBuf o_rgb[2], o_depth[2], o_alpha[2], o_u8[2], o_nc[2];
+    DevBuf o_pack[2];                  // ONE block per set holding every requested host output (sas_packed_layout)
+    DevBuf o_rgb[1], o_alpha[1];       // nerfstudio post-processing scratch when rgb / alpha are not requested themselves
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t render_done[2] = {}, copy_done[2] = {};
     unsigned long long async_seq = 0;    // async renders issued so far; render k uses staging set k & 1
-    long long max_isects = 0;
+    unsigned long long async_render_seq[2] = {0, 0};  // position of the async render of each set among all renders
+    long long max_isects = 0;          // capacity of the merged id list (entries of 4 B)
+    long long max_isects_src = 0;      // capacity of the bucket entries (pairs and their sort buffer, 8 B each)
     SasCounters *counters = nullptr;
+    // overflow reporting without a sync per frame: every render snapshots its counters into a device ring; host-output
+    // renders bring their slot back with the observation (sas_common.cuh SasSnapRing)
+    SasSnapRing *snap = nullptr;
+    SasSnapRing *h_snap = nullptr;       // pinned host copy
+    unsigned long long render_seq = 0;   // renders issued (== ring->seq once they have run)
+    unsigned long long ovf_floor = 0;    // renders before this one are not reported any more (reserve / poll)
+    int max_env_index = 0;               // largest env an image of the current camera set refers to
     bool rendered = false;
     int last_launches = 0;
     bool stage_timing = false;
@@ -69,8 +79,8 @@ struct sas_renderer {
     struct GraphKey {
         int I, C, W, H, ns, flags;
         float bg[3];
-        void *rgb, *depth, *alpha, *u8, *nc;
-        long long max_isects;
+        void *rgb, *depth, *alpha, *u8, *nc, *f16;
+        long long max_isects, max_isects_src;
         unsigned long long buf_gen;
     };
     // two cached graphs (the async host path alternates between two output sets), least recently used replaced
@@ -124,15 +134,45 @@ void free_buf(DevBuf &b) {
     b.p = nullptr; b.bytes = 0;
 }
 
-int ensure_isects(sas_renderer *r, long long m) {
-    if (m > 0x7ffffff0ll) m = 0x7ffffff0ll;
-    if (m <= r->max_isects && r->pairs.p) return SAS_OK;
+// m_src bucket entries (pairs + sort buffer), m_all merged ids; 0 = leave as it is.  Offsets are int32.
+int ensure_isects(sas_renderer *r, long long m_src, long long m_all) {
+    if (m_src > 0x7ffffff0ll) m_src = 0x7ffffff0ll;
+    if (m_all > 0x7ffffff0ll) m_all = 0x7ffffff0ll;
     int rc;
-    if ((rc = ensure(r, r->pairs, (size_t)m * sizeof(uint2)))) return rc;
-    if ((rc = ensure(r, r->pairs_alt, (size_t)m * sizeof(uint2)))) return rc;
-    if ((rc = ensure(r, r->merged, (size_t)m * sizeof(int)))) return rc;
-    r->max_isects = m;
+    if (m_src > r->max_isects_src || (m_src > 0 && !r->pairs.p)) {
+        if ((rc = ensure(r, r->pairs, (size_t)m_src * sizeof(uint2)))) return rc;
+        if ((rc = ensure(r, r->pairs_alt, (size_t)m_src * sizeof(uint2)))) return rc;
+        r->max_isects_src = m_src;
+    }
+    if (m_all > r->max_isects || (m_all > 0 && !r->merged.p)) {
+        if ((rc = ensure(r, r->merged, (size_t)m_all * sizeof(int)))) return rc;
+        r->max_isects = m_all;
+    }
+    r->ovf_floor = r->render_seq;  // earlier overflows have been answered
     return SAS_OK;
+}
+
+struct PackedLayout {
+    size_t off[6] = {0, 0, 0, 0, 0, 0};
+    size_t total = 0;
+};
+// order and element sizes of the SAS_OUT_* bits: u8 rgb (3), f16 depth (2), f32 depth (4), alpha (4), rgb (12), n_contrib (4)
+PackedLayout packed_layout(size_t P, int want) {
+    static const size_t kBytes[6] = {3, 2, 4, 4, 12, 4};
+    PackedLayout l;
+    for (int k = 0; k < 6; k++)
+        if (want & (1 << k)) {
+            l.off[k] = l.total;
+            l.total = (l.total + P * kBytes[k] + 255) & ~(size_t)255;
+        }
+    return l;
+}
+
+int overflow_error(sas_renderer *r, const SasCounters &c, const char *who) {
+    char buf[320];
+    snprintf(buf, sizeof(buf), "%s: the frame is INCOMPLETE, intersection buffers overflowed (bucket entries %llu of capacity %lld, merged "
+             "ids %llu of capacity %lld): sas_reserve_isects2 and render again", who, c.n_isects_src, r->max_isects_src, c.n_isects, r->max_isects);
+    return fail(r, SAS_ECAPACITY, buf);
 }
 
 void fill_camera(SasCamera &c, const float *vm, const float *K, int width, int height, int env) {
@@ -162,14 +202,23 @@ int sas_variant_flags() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SAS_VARIANT");
-        v = e ? (int)strtol(e, nullptr, 0) & 0x3ff : 0x2cf;
+        v = e ? (int)strtol(e, nullptr, 0) & 0xfff : 0x2cf;
     }
     return v;
 }
 
 extern "C" {
 
-const char *sas_version(void) { return "sas_b200 0.3.0 (sm_100a)"; }
+const char *sas_version(void) { return "sas_b200 0.4.0 (sm_100a)"; }
+
+int sas_packed_layout(int n_images, int width, int height, int want, size_t offsets[6], size_t *total_bytes) {
+    if (n_images <= 0 || width <= 0 || height <= 0 || !offsets || !total_bytes || (want & ~63)) return SAS_EINVAL;
+    const PackedLayout l = packed_layout((size_t)n_images * width * height, want);
+    for (int k = 0; k < 6; k++)
+        if (want & (1 << k)) offsets[k] = l.off[k];
+    *total_bytes = l.total;
+    return SAS_OK;
+}
 
 const char *sas_last_error(const sas_renderer *r) { return r ? r->err.c_str() : g_create_error.c_str(); }
 
@@ -249,7 +298,13 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(cudaMemcpy(r->sh_planes, p_sh.data(), sizeof(float) * p_sh.size(), cudaMemcpyHostToDevice));
 
     const int maxE = cfg->max_envs > 0 ? cfg->max_envs : 1;
-    if (r->L > 0) SAS_CUDA_C(cudaMalloc(&r->link_poses, sizeof(float) * 12 * (size_t)maxE * r->L));
+    if (r->L > 0) {
+        // identity until sas_set_link_poses: an env that has never been given poses renders its links at rest
+        std::vector<float> ident((size_t)12 * maxE * r->L, 0.0f);
+        for (size_t k = 0; k < (size_t)maxE * r->L; k++) ident[12 * k] = ident[12 * k + 4] = ident[12 * k + 8] = 1.0f;
+        SAS_CUDA_C(cudaMalloc(&r->link_poses, sizeof(float) * ident.size()));
+        SAS_CUDA_C(cudaMemcpy(r->link_poses, ident.data(), sizeof(float) * ident.size(), cudaMemcpyHostToDevice));
+    }
     SAS_CUDA_C(cudaMalloc(&r->row_cams, sizeof(SasCamera) * 2 * cfg->max_images));
     SAS_CUDA_C(cudaMalloc(&r->view_of_image, sizeof(int) * cfg->max_images));
     r->stage_bytes = sizeof(SasCamera) * 2 * cfg->max_images + sizeof(int) * cfg->max_images;
@@ -261,8 +316,12 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     for (cudaEvent_t &ev : r->span_ev) SAS_CUDA_C(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SAS_CUDA_C(cudaMalloc(&r->counters, sizeof(SasCounters) + sizeof(SasWork)));  // SasWork follows the counters
     SAS_CUDA_C(cudaMemset(r->counters, 0, sizeof(SasCounters) + sizeof(SasWork)));
-    long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
-    SAS_TRY(ensure_isects(r, m));
+    SAS_CUDA_C(cudaMalloc(&r->snap, sizeof(SasSnapRing)));
+    SAS_CUDA_C(cudaMemset(r->snap, 0, sizeof(SasSnapRing)));
+    SAS_CUDA_C(cudaMallocHost(&r->h_snap, sizeof(SasSnapRing)));
+    memset(r->h_snap, 0, sizeof(SasSnapRing));
+    const long long m = cfg->max_isects > 0 ? cfg->max_isects : (long long)1 << 22;
+    SAS_TRY(ensure_isects(r, cfg->max_isects_src > 0 ? cfg->max_isects_src : m, m));
 #undef SAS_TRY
 #undef SAS_CUDA_C
     *out = r;
@@ -275,7 +334,8 @@ void sas_destroy(sas_renderer *r) {
     cudaDeviceSynchronize();
     cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
     cudaFree(r->fk_dev);
-    cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters);
+    cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters); cudaFree(r->snap);
+    if (r->h_snap) cudaFreeHost(r->h_snap);
     if (r->stage_host) cudaFreeHost(r->stage_host);
     if (r->cams_copied) cudaEventDestroy(r->cams_copied);
     for (cudaEvent_t ev : r->stage_ev)
@@ -296,8 +356,7 @@ void sas_destroy(sas_renderer *r) {
     for (cudaEvent_t ev : r->copy_done)
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
-                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_depth[0], &r->o_alpha[0], &r->o_u8[0], &r->o_nc[0],
-                      &r->o_rgb[1], &r->o_depth[1], &r->o_alpha[1], &r->o_u8[1], &r->o_nc[1],
+                      &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_alpha[0], &r->o_pack[0], &r->o_pack[1],
                       &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
@@ -306,7 +365,13 @@ void sas_destroy(sas_renderer *r) {
 int sas_reserve_isects(sas_renderer *r, long long max_isects) {
     if (!r || max_isects <= 0) return fail(r, SAS_EINVAL, "sas_reserve_isects: bad argument");
     SAS_CUDA(r, cudaSetDevice(r->device));
-    return ensure_isects(r, max_isects);
+    return ensure_isects(r, max_isects, max_isects);
+}
+
+int sas_reserve_isects2(sas_renderer *r, long long max_src, long long max_all) {
+    if (!r || max_src < 0 || max_all < 0) return fail(r, SAS_EINVAL, "sas_reserve_isects2: bad argument");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    return ensure_isects(r, max_src, max_all);
 }
 
 int sas_set_link_poses(sas_renderer *r, const float *poses, int n_envs, int mem, void *stream) {
@@ -401,9 +466,11 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     if (width > r->cfg.max_width || height > r->cfg.max_height || width > 4080 || height > 4080)
         return fail(r, SAS_ECAPACITY, "sas_set_cameras: image size exceeds max_width/max_height");
     const int maxE = r->cfg.max_envs > 0 ? r->cfg.max_envs : 1;
+    int max_env = 0;
     for (int i = 0; i < n_images; i++) {
         const int env = env_of_image ? env_of_image[i] : 0;
         if (env < 0 || (r->L > 0 && env >= maxE)) return fail(r, SAS_EINVAL, "sas_set_cameras: env_of_image out of range");
+        if (env > max_env) max_env = env;
     }
     SAS_CUDA(r, cudaSetDevice(r->device));
     SAS_CUDA(r, cudaEventSynchronize(r->cams_copied));  // previous staging copy finished
@@ -439,6 +506,7 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
     SAS_CUDA(r, cudaMemcpyAsync(r->view_of_image, voi, sizeof(int) * (size_t)n_images, cudaMemcpyHostToDevice, st));
     SAS_CUDA(r, cudaEventRecord(r->cams_copied, st));
     r->I = n_images; r->C = C; r->W = width; r->H = height;
+    r->max_env_index = max_env;
     r->tile_w = (width + SAS_TILE - 1) / SAS_TILE;
     r->tile_h = (height + SAS_TILE - 1) / SAS_TILE;
     r->cameras_set = true;
@@ -470,7 +538,8 @@ int sas_set_cameras(sas_renderer *r, const float *viewmats, const float *Ks, con
 // Enqueues the device work of one render on st (no host synchronisation, no allocation): the part that is
 // captured into a CUDA graph.
 static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb, float *d_depth, float *d_alpha, uint8_t *d_u8, int *d_nc,
-                          cudaStream_t st, int *n_launches) {
+                          uint16_t *d_f16, cudaStream_t st, int *n_launches) {
+    const long long cap_src = r->max_isects_src, cap_all = r->max_isects;
     const int I = r->I, C = r->C, W = r->W, H = r->H, tw = r->tile_w, th = r->tile_h, T = tw * th;
     const size_t RT = (size_t)(C + I) * T, IT = (size_t)I * T;
     const bool ns = out->nerfstudio_post != 0;
@@ -523,9 +592,9 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(1);
     if (sas_scan_lists_fused_ok(C, I, T)) {
-        SAS_CUDA(r, sas_launch_scan_lists_fused(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, roff, ioff, r->counters, r->max_isects,
-                                                work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p, (int *)r->comp_list.p, st,
-                                                &launches));
+        SAS_CUDA(r, sas_launch_scan_lists_fused(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, roff, ioff, r->counters, cap_src,
+                                                cap_all, work, (unsigned char *)r->view_needed.p, (int *)r->sort_list.p,
+                                                (int *)r->comp_list.p, st, &launches));
     } else {
         // The two scans and the work lists only read the counts (and the group masks): three independent chains of
         // 3 + 3 + 4 small kernels.  Forked onto side streams they cost the longest chain instead of the sum
@@ -538,8 +607,8 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
             SAS_CUDA(r, cudaStreamWaitEvent(s_b, r->scan_ev[0], 0));
             SAS_CUDA(r, cudaStreamWaitEvent(s_w, r->scan_ev[0], 0));
         }
-        SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, bs_a, r->counters, r->max_isects, st, &launches));
-        SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, bs_b, r->counters, r->max_isects, s_b, &launches));
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)RT, nullptr, C, T, roff, bs_a, r->counters, cap_src, st, &launches));
+        SAS_CUDA(r, sas_launch_scan(rcount, (int)IT, r->view_of_image, C, T, ioff, bs_b, r->counters, cap_all, s_b, &launches));
         SAS_CUDA(r, sas_launch_work_lists(rcount, r->view_of_image, dyn_mask, C, I, W, H, tw, th, work, (unsigned char *)r->view_needed.p,
                                           (int *)r->sort_list.p, (int *)r->comp_list.p, s_w, &launches));
         if (fork) {
@@ -553,30 +622,32 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     if (two_spans) SAS_CUDA(r, fork_span());
     for (const SasRowSpan &sp : {span_bg, span_dy}) {
         if (sp.n <= 0) continue;
-        SAS_CUDA(r, sas_launch_emit(bins, sp, tw, th, roff, rcursor, pairs, r->max_isects, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
+        SAS_CUDA(r, sas_launch_emit(bins, sp, tw, th, roff, rcursor, pairs, cap_src, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
         launches += 1;
     }
     if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, r->max_isects, st, r->aux, r->fork_ev,
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, cap_src, st, r->aux, r->fork_ev,
                                      &launches));
-    SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, r->max_isects, r->max_isects,
+    SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, cap_src, cap_all,
                                  (sas_variant_flags() & 8) ? 0 : 1, (const int *)r->comp_list.p, work, st));
     launches += 1;
     SAS_STAGE(4);
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
-    const SasOutputs img_out{d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc};
+    const SasOutputs img_out{d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, d_f16};
     const SasViewBuf view_out{(float *)r->v_acc.p, (float *)r->v_depth.p, (int *)r->v_nc.p};
     SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, dyn_mask, (const int *)r->comp_list.p, work,
-                                     r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, r->max_isects, r->max_isects,
+                                     r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, cap_src, cap_all,
                                      r->counters, st, &launches));
     SAS_STAGE(5);
     if (ns) {
-        SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, I, W, H, out->background[0], out->background[1],
+        SAS_CUDA(r, sas_launch_ns_post(d_rgb, d_depth, d_alpha, d_u8, d_f16, I, W, H, out->background[0], out->background[1],
                                        out->background[2], (unsigned *)r->img_max.p, st, &launches));
     }
     SAS_STAGE(6);
+    SAS_CUDA(r, sas_launch_snapshot(r->counters, r->snap, st));  // this render's counters -> ring[seq & 3]
+    launches += 1;
 #undef SAS_STAGE
     *n_launches = launches;
     return SAS_OK;
@@ -593,8 +664,11 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     float *d_rgb = out->rgb, *d_depth = out->depth, *d_alpha = out->alpha;
     uint8_t *d_u8 = out->rgb_u8;
     int *d_nc = out->n_contrib;
+    uint16_t *d_f16 = out->depth_f16;
     if (out->mem != SAS_MEM_HOST && out->mem != SAS_MEM_DEVICE && out->mem != SAS_MEM_HOST_ASYNC)
         return fail(r, SAS_EINVAL, "sas_render: outputs.mem must be SAS_MEM_HOST, SAS_MEM_DEVICE or SAS_MEM_HOST_ASYNC");
+    if (r->L > 0 && r->max_env_index >= r->n_envs)
+        return fail(r, SAS_ESTATE, "sas_render: an image refers to an env beyond the n_envs given to sas_set_link_poses");
     const bool async_out = out->mem == SAS_MEM_HOST_ASYNC;
     const bool host_out = out->mem == SAS_MEM_HOST || async_out;
     const bool ns = out->nerfstudio_post != 0;
@@ -605,13 +679,24 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         for (cudaEvent_t &ev : r->render_done) SAS_CUDA(r, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (cudaEvent_t &ev : r->copy_done) SAS_CUDA(r, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
+    // host outputs: ONE device staging block per set, laid out by sas_packed_layout
+    void *const h_ptr[6] = {out->rgb_u8, out->depth_f16, out->depth, out->alpha, out->rgb, out->n_contrib};
+    int want = 0;
+    PackedLayout lay;
     if (host_out) {
-        if (out->rgb || ns) { if ((rc = ensure(r, r->o_rgb[set], P * 12))) return rc; d_rgb = (float *)r->o_rgb[set].p; }
-        if (out->depth) { if ((rc = ensure(r, r->o_depth[set], P * 4))) return rc; d_depth = (float *)r->o_depth[set].p; }
-        if (out->alpha || ns) { if ((rc = ensure(r, r->o_alpha[set], P * 4))) return rc; d_alpha = (float *)r->o_alpha[set].p; }
-        if (out->rgb_u8) { if ((rc = ensure(r, r->o_u8[set], P * 3))) return rc; d_u8 = (uint8_t *)r->o_u8[set].p; }
-        if (out->n_contrib) { if ((rc = ensure(r, r->o_nc[set], P * 4))) return rc; d_nc = (int *)r->o_nc[set].p; }
-    } else if (ns) {
+        for (int k = 0; k < 6; k++)
+            if (h_ptr[k]) want |= 1 << k;
+        lay = packed_layout(P, want);
+        if ((rc = ensure(r, r->o_pack[set], lay.total))) return rc;
+        unsigned char *base = (unsigned char *)r->o_pack[set].p;
+        d_u8 = out->rgb_u8 ? (uint8_t *)(base + lay.off[0]) : nullptr;
+        d_f16 = out->depth_f16 ? (uint16_t *)(base + lay.off[1]) : nullptr;
+        d_depth = out->depth ? (float *)(base + lay.off[2]) : nullptr;
+        d_alpha = out->alpha ? (float *)(base + lay.off[3]) : nullptr;
+        d_rgb = out->rgb ? (float *)(base + lay.off[4]) : nullptr;
+        d_nc = out->n_contrib ? (int *)(base + lay.off[5]) : nullptr;
+    }
+    if (ns) {  // the post-processing needs rgb and alpha even when the caller does not ask for them
         if (!d_rgb) { if ((rc = ensure(r, r->o_rgb[0], P * 12))) return rc; d_rgb = (float *)r->o_rgb[0].p; }
         if (!d_alpha) { if ((rc = ensure(r, r->o_alpha[0], P * 4))) return rc; d_alpha = (float *)r->o_alpha[0].p; }
     }
@@ -636,8 +721,8 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         memset(&key, 0, sizeof(key));  // padding bytes take part in the memcmp below
         key.I = r->I; key.C = r->C; key.W = r->W; key.H = r->H; key.ns = ns ? 1 : 0; key.flags = sas_variant_flags();
         for (int k = 0; k < 3; k++) key.bg[k] = out->background[k];
-        key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc;
-        key.max_isects = r->max_isects; key.buf_gen = r->buf_gen;
+        key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc; key.f16 = d_f16;
+        key.max_isects = r->max_isects; key.max_isects_src = r->max_isects_src; key.buf_gen = r->buf_gen;
         sas_renderer::GraphSlot *slot = nullptr;
         for (auto &g : r->graphs)
             if (g.exec && memcmp(&key, &g.key, sizeof(key)) == 0) slot = &g;
@@ -649,7 +734,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
             memcpy(&r->pending_key[r->pending_next], &key, sizeof(key));
             r->pending_valid[r->pending_next] = true;
             r->pending_next ^= 1;
-            if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
+            if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, d_f16, st, &launches))) return rc;
         } else {
             if (!slot) {
                 slot = &r->graphs[0];
@@ -657,7 +742,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
                 if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 SAS_CUDA(r, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-                rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches);
+                rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, d_f16, st, &launches);
                 cudaError_t ce = cudaStreamEndCapture(st, &graph);
                 if (rc != SAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess) return fail(r, SAS_ECUDA, std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
@@ -675,10 +760,11 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
             launches = slot->launches;
         }
     } else {
-        if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, st, &launches))) return rc;
+        if ((rc = enqueue_render(r, out, d_rgb, d_depth, d_alpha, d_u8, d_nc, d_f16, st, &launches))) return rc;
     }
     r->last_launches = launches;
     r->rendered = true;
+    const unsigned long long seq = r->render_seq++;   // this render's snapshot slot is seq & 3
     if (host_out) {
         // async: the copies run on the library's copy stream behind an event, so the caller's stream is free for the
         // next render; nothing synchronises here (sas_wait_outputs does)
@@ -687,16 +773,35 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
             SAS_CUDA(r, cudaEventRecord(r->render_done[set], st));
             SAS_CUDA(r, cudaStreamWaitEvent(cs, r->render_done[set], 0));
         }
-        if (out->rgb) SAS_CUDA(r, cudaMemcpyAsync(out->rgb, d_rgb, P * 12, cudaMemcpyDeviceToHost, cs));
-        if (out->depth) SAS_CUDA(r, cudaMemcpyAsync(out->depth, d_depth, P * 4, cudaMemcpyDeviceToHost, cs));
-        if (out->alpha) SAS_CUDA(r, cudaMemcpyAsync(out->alpha, d_alpha, P * 4, cudaMemcpyDeviceToHost, cs));
-        if (out->rgb_u8) SAS_CUDA(r, cudaMemcpyAsync(out->rgb_u8, d_u8, P * 3, cudaMemcpyDeviceToHost, cs));
-        if (out->n_contrib) SAS_CUDA(r, cudaMemcpyAsync(out->n_contrib, d_nc, P * 4, cudaMemcpyDeviceToHost, cs));
+        // one copy when the caller's host buffers are one block with the staging layout, else one per output
+        const unsigned char *d_base = (const unsigned char *)r->o_pack[set].p;
+        int first = -1;
+        bool packed = want != 0;
+        for (int k = 0; k < 6 && packed; k++)
+            if (want & (1 << k)) {
+                if (first < 0) first = k;
+                packed = (unsigned char *)h_ptr[k] - (unsigned char *)h_ptr[first] == (ptrdiff_t)(lay.off[k] - lay.off[first]);
+            }
+        static const size_t kBytes[6] = {3, 2, 4, 4, 12, 4};
+        if (packed) {
+            int last = first;
+            for (int k = 0; k < 6; k++)
+                if (want & (1 << k)) last = k;
+            SAS_CUDA(r, cudaMemcpyAsync(h_ptr[first], d_base + lay.off[first], lay.off[last] + P * kBytes[last] - lay.off[first],
+                                        cudaMemcpyDeviceToHost, cs));
+        } else {
+            for (int k = 0; k < 6; k++)
+                if (want & (1 << k)) SAS_CUDA(r, cudaMemcpyAsync(h_ptr[k], d_base + lay.off[k], P * kBytes[k], cudaMemcpyDeviceToHost, cs));
+        }
+        // this render's counter snapshot travels with the observation (the ring slot stays valid for 3 more renders)
+        SAS_CUDA(r, cudaMemcpyAsync(&r->h_snap->slot[seq & 3ull], &r->snap->slot[seq & 3ull], sizeof(SasCounters), cudaMemcpyDeviceToHost, cs));
         if (async_out) {
             SAS_CUDA(r, cudaEventRecord(r->copy_done[set], cs));
+            r->async_render_seq[set] = seq;
             r->async_seq++;
         } else {
             SAS_CUDA(r, cudaStreamSynchronize(st));
+            if (seq >= r->ovf_floor && r->h_snap->slot[seq & 3ull].overflow) return overflow_error(r, r->h_snap->slot[seq & 3ull], "sas_render");
         }
     }
     return SAS_OK;
@@ -708,7 +813,34 @@ int sas_wait_outputs(sas_renderer *r, int age) {
     if (r->async_seq <= (unsigned long long)age) return fail(r, SAS_ESTATE, "sas_wait_outputs: no such SAS_MEM_HOST_ASYNC render was issued");
     SAS_CUDA(r, cudaSetDevice(r->device));
     SAS_CUDA(r, cudaEventSynchronize(r->copy_done[(r->async_seq - 1 - age) & 1u]));
+    // the async renders are the last renders issued on this handle unless other modes were mixed in: find the snapshot
+    // of this one by its position among ALL renders (async_render_seq remembers the last two)
+    const unsigned long long seq = r->async_render_seq[(r->async_seq - 1 - age) & 1u];
+    if (seq >= r->ovf_floor && r->h_snap->slot[seq & 3ull].overflow) return overflow_error(r, r->h_snap->slot[seq & 3ull], "sas_wait_outputs");
     return SAS_OK;
+}
+
+int sas_poll_overflow(sas_renderer *r, long long *need_src, long long *need_all, void *stream) {
+    if (!r) return SAS_EINVAL;
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SAS_CUDA(r, cudaMemcpyAsync(r->h_snap, r->snap, sizeof(SasSnapRing), cudaMemcpyDeviceToHost, st));
+    SAS_CUDA(r, cudaStreamSynchronize(st));
+    const unsigned long long done = r->h_snap->seq;  // renders that have run
+    long long ns = 0, na = 0;
+    int any = 0;
+    for (unsigned long long k = done > 4 ? done - 4 : 0; k < done; k++) {
+        if (k < r->ovf_floor) continue;
+        const SasCounters &c = r->h_snap->slot[k & 3ull];
+        if (!c.overflow) continue;
+        any = 1;
+        if ((long long)c.n_isects_src > ns) ns = (long long)c.n_isects_src;
+        if ((long long)c.n_isects > na) na = (long long)c.n_isects;
+    }
+    r->ovf_floor = done;
+    if (need_src) *need_src = ns;
+    if (need_all) *need_all = na;
+    return any;
 }
 
 int sas_set_stage_timing(sas_renderer *r, int enable) {
@@ -742,6 +874,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
     out->n_staged = (int64_t)(c.n_staged / 8);  // the compositor counts per strip of WARPS/8 of a tile
     out->max_tile_list = (int64_t)c.max_tile_list;
     out->overflow = (int32_t)c.overflow;
+    out->cap_isects = r->max_isects; out->cap_isects_src = r->max_isects_src;
     out->n_images = r->I; out->n_views = r->C; out->n_gaussians = r->N; out->n_background = r->n_bg;
     out->width = r->W; out->height = r->H; out->tile_w = r->tile_w; out->tile_h = r->tile_h;
     return SAS_OK;
@@ -775,7 +908,7 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
             // the render skips the id lists of tiles without link Gaussians (the compositor takes those from the
             // view's bucket); produce them now
             SAS_CUDA(r, sas_launch_merge((const uint2 *)r->pairs.p, (const int *)r->row_tile_offset.p, (const int *)r->img_tile_offset.p,
-                                         r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects, r->max_isects, 1, nullptr, nullptr, 0));
+                                         r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects_src, r->max_isects, 1, nullptr, nullptr, 0));
             SAS_CUDA(r, cudaDeviceSynchronize());
             src = r->merged.p; avail = (size_t)m * 4;
             break;

@@ -194,6 +194,8 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //   bit 7  compositor: warp -> footprint map rotated with the work-item index (evens out the four schedulers)
 //   bit 8  scans + work lists as eleven small kernels even when the single-CTA fused kernel applies
 //   bit 9  compositor: the groups link Gaussians can reach packed four per warp, a tile = one or two CTAs of 4 warps
+//   bit 10 compositor (with bit 9): "split" -- alpha evaluated record-parallel (lane = hit, 8 pixels each), only the
+//          transmittance chain serial per pixel (sas_composite.cu MODE 3)
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -202,6 +204,7 @@ struct SasOutputs {
     float *rgb, *depth, *alpha;
     uint8_t *rgb_u8;
     int *n_contrib;
+    uint16_t *depth_f16;  // IEEE binary16 bits of depth
 };
 // ... and the per-view buffers holding the background-only tiles shared by the images of a view.
 struct SasViewBuf {
@@ -228,8 +231,11 @@ cudaError_t sas_launch_work_lists(const unsigned int *row_tile_count, const int 
 bool sas_scan_lists_fused_ok(int C, int I, int T);
 cudaError_t sas_launch_scan_lists_fused(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C,
                                         int I, int W, int H, int tile_w, int tile_h, int *row_tile_offset, int *img_tile_offset,
-                                        SasCounters *counters, long long capacity, SasWork *work, unsigned char *view_tile_needed,
-                                        int *sort_list, int *comp_list, cudaStream_t st, int *n_launches);
+                                        SasCounters *counters, long long cap_src, long long cap_all, SasWork *work,
+                                        unsigned char *view_tile_needed, int *sort_list, int *comp_list, cudaStream_t st, int *n_launches);
+// counters of this render -> ring[seq & 3], ++seq (device-side; the last node of a render, inside the CUDA graph)
+struct SasSnapRing { SasCounters slot[4]; unsigned long long seq; };
+cudaError_t sas_launch_snapshot(const SasCounters *counters, SasSnapRing *ring, cudaStream_t st);
 cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const float4 *scale_link, const float *sh_planes,
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
@@ -257,5 +263,5 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,
                                  int *n_launches);
-cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
-                               float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);
+cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, uint16_t *depth_f16, int I, int W, int H,
+                               float bg0, float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches);

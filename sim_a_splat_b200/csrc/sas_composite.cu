@@ -42,6 +42,8 @@
 // DESIGN.md "What bounds the compositor" and "Experiments that did not pay" list what was measured.
 #include "sas_common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 namespace {
@@ -171,12 +173,168 @@ __device__ __forceinline__ void process_batch(const SasRecord *sb, const unsigne
     }
 }
 
+// ---- MODE 3: "split" compositor -- only the transmittance chain is serial ------------------------------------------
+// sigma, exp and alpha of a (pixel, record) pair do not depend on the pixel's transmittance T; only
+// T' = T (1 - alpha), the T' <= 1e-4 stop test and the accumulation do.  MODE 2 evaluates all of it inside the
+// per-group walk (lane = pixel): 18 of 32 lanes active per instruction, 7 of 32 while blending, ~220 cycles per
+// dependent walk iteration (profiles/r01e_ncu_composite.txt).  Here a staged batch is processed per warp in two
+// phases over the warp's (record, group) HITS -- the records whose culling box reaches one of the warp's four
+// packed 4x2 groups, queued in (group, record) order:
+//   phase A (lane = hit): sigma, exp, alpha for the group's 8 pixels of one hit per lane -- 32 hits side by
+//     side, no divergence, 8 independent chains per lane; alpha rows (0 where the pair fails the range or the
+//     alpha >= 1/255 test) and the hit's colour go to a per-warp scratch in shared memory, and 8 ballots turn the
+//     pass bits into one 32-hit mask PER PIXEL;
+//   phase B (lane = pixel): every pixel walks only ITS OWN passing hits, in order: one LDS of alpha, one LDS.128 of
+//     the colour, T' = T (1 - alpha), the stop test, four FMAs -- ~6 dependent operations per hit.
+// Every pixel performs exactly the operations MODE 2 (and the oracle) performs for it, in the same order, so the
+// images stay bit-identical.
+struct __align__(16) SplitScratch {   // per warp
+    float alpha[32][8];               // alpha of hit k (row) for the 8 pixels of its group; 0 = does not contribute
+    float4 col[32];                   // r, g, b, depth of hit k
+    uint4 hitmask[4];                 // [group]: 4 x 32-record chunk masks of the batch: records whose culling box reaches the group
+};
+
+// position of the r-th (0-based) set bit of w; requires r < popc(w)
+__device__ __forceinline__ unsigned sas_nth_set_bit(unsigned w, unsigned r) {
+    unsigned pos = 0u, c;
+    c = __popc(w & 0xffffu); if (r >= c) { r -= c; pos = 16u; w >>= 16; }
+    c = __popc(w & 0xffu);   if (r >= c) { r -= c; pos += 8u; w >>= 8; }
+    c = __popc(w & 0xfu);    if (r >= c) { r -= c; pos += 4u; w >>= 4; }
+    c = __popc(w & 0x3u);    if (r >= c) { r -= c; pos += 2u; w >>= 2; }
+    c = w & 1u;              if (r >= c) pos += 1u;
+    return pos;
+}
+
+__device__ __forceinline__ float sas_lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 sas_lds_f32x4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// an opaque copy of a 32-bit value: the compiler cannot rematerialise it from its inputs (it otherwise recomputes
+// shared-memory addresses -- S2R included -- inside the walk loop when registers are tight)
+__device__ __forceinline__ unsigned sas_pin(unsigned v) {
+    unsigned r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// a_addr: shared address of ws.alpha[0][this lane's pixel], c_addr: of ws.col[0] (both pinned by the caller)
+template <bool COUNT>
+__device__ __forceinline__ void process_batch_split(const SasRecord *sb, const unsigned *s_reach, unsigned gbits, int cnt, Pixel &p,
+                                                    SplitScratch &ws, const float2 *s_org, unsigned a_addr, unsigned c_addr) {
+    const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+    const unsigned dm = __ballot_sync(0xffffffffu, p.done());
+    if (dm == 0xffffffffu) return;
+    // hit masks: bit l of word c of group g = record 32 c + l of the batch reaches group g (its culling box);
+    // groups whose pixels have all finished drop out.  ng[g] = hits of group g in this batch.
+    unsigned ng[4] = {0u, 0u, 0u, 0u};
+    uint4 mym = make_uint4(0u, 0u, 0u, 0u);  // lane g < 4 collects the four chunk masks of group g
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned rb = (c * 32 + lane < cnt) ? s_reach[c * 32 + lane] : 0u;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            unsigned b = __ballot_sync(0xffffffffu, (rb >> ((gbits >> (8 * g)) & 31u)) & 1u);
+            if (((dm >> (8 * g)) & 0xffu) == 0xffu) b = 0u;
+            ng[g] += __popc(b);
+            if (lane == g) { if (c == 0) mym.x = b; else if (c == 1) mym.y = b; else if (c == 2) mym.z = b; else mym.w = b; }
+        }
+    }
+    const unsigned b1 = ng[0], b2 = b1 + ng[1], b3 = b2 + ng[2], h = b3 + ng[3];  // first hit index of groups 1..3, total
+    if (h == 0) return;
+    if (lane < 4) ws.hitmask[lane] = mym;
+    // hits are numbered in (group, record) order and taken 32 per round; this lane's group owns hits [my_lo, my_hi)
+    const unsigned my_lo = grp == 0 ? 0u : grp == 1 ? b1 : grp == 2 ? b2 : b3;
+    const unsigned my_hi = grp == 0 ? b1 : grp == 1 ? b2 : grp == 2 ? b3 : h;
+    __syncwarp();
+    for (unsigned k0 = 0; k0 < h; k0 += 32) {
+        // ---- phase A: lane = hit k ----
+        const unsigned k = k0 + lane;
+        unsigned pass8 = 0u;
+        if (k < h) {
+            // hit k -> (group g, rank r among g's hits) -> (chunk, r-th set bit) -> record of the batch
+            const unsigned g = (k >= b1 ? 1u : 0u) + (k >= b2 ? 1u : 0u) + (k >= b3 ? 1u : 0u);
+            unsigned r = k - (g == 0u ? 0u : g == 1u ? b1 : g == 2u ? b2 : b3);
+            const uint4 wm = ws.hitmask[g];
+            const unsigned p0 = __popc(wm.x), p1 = p0 + __popc(wm.y), p2 = p1 + __popc(wm.z);
+            unsigned w = wm.x, jb = 0u, sub = 0u;
+            if (r >= p0) { w = wm.y; jb = 32u; sub = p0; }
+            if (r >= p1) { w = wm.z; jb = 64u; sub = p1; }
+            if (r >= p2) { w = wm.w; jb = 96u; sub = p2; }
+            const SasRecord *rc = sb + (jb + sas_nth_set_bit(w, r - sub));
+            const float4 A = rc->a;
+            const float2 B = *reinterpret_cast<const float2 *>(&rc->b);  // conic c / 2, opacity
+            const float2 o = s_org[g];                                   // centre of the group's first pixel
+            float dxv[4], al[8];
+#pragma unroll
+            for (int ix = 0; ix < 4; ix++) dxv[ix] = A.x - (o.x + (float)ix);
+#pragma unroll
+            for (int iy = 0; iy < 2; iy++) {
+                const float dy = A.y - (o.y + (float)iy);
+                const float t1 = A.w * dy, t2 = (B.x * dy) * dy;
+#pragma unroll
+                for (int ix = 0; ix < 4; ix++) {
+                    const float sigma = fmaf(fmaf(A.z, dxv[ix], t1), dxv[ix], t2);
+                    const float a0 = fminf(SAS_ALPHA_MAX, B.y * sas_exp_neg_small(-sigma));
+                    const bool ok = (__float_as_uint(sigma) <= __float_as_uint(SAS_SIGMA_SKIP)) && (a0 >= SAS_ALPHA_MIN);
+                    al[iy * 4 + ix] = ok ? a0 : 0.0f;
+                    pass8 |= ok ? (1u << (iy * 4 + ix)) : 0u;
+                }
+            }
+            float4 *row = reinterpret_cast<float4 *>(ws.alpha[lane]);
+            row[0] = make_float4(al[0], al[1], al[2], al[3]);
+            row[1] = make_float4(al[4], al[5], al[6], al[7]);
+            if (pass8) ws.col[lane] = rc->c;
+        }
+        // one 32-hit mask per pixel: bit kk = hit k0 + kk passes at THIS lane's pixel
+        unsigned mine = 0u;
+#pragma unroll
+        for (int pp = 0; pp < 8; pp++) {
+            const unsigned b = __ballot_sync(0xffffffffu, (pass8 >> pp) & 1u);
+            if (gl == pp) mine = b;
+        }
+        {   // ... restricted to the hits of this lane's group
+            const int lo = max((int)my_lo - (int)k0, 0), hi = min((int)my_hi - (int)k0, 32);
+            mine = hi > lo ? (mine & ((0xffffffffu >> (32 - (hi - lo))) << lo)) : 0u;
+        }
+        if (p.done()) mine = 0u;
+        __syncwarp();  // alpha rows and colours are visible to the warp
+        // ---- phase B: lane = pixel, only the transmittance chain ----
+        while (mine) {
+            const unsigned kk = (unsigned)__ffs(mine) - 1u;
+            mine &= mine - 1u;
+            const float a = sas_lds_f32(a_addr + kk * 32u);
+            const float nT = p.T * (1.0f - a);
+            if (nT <= SAS_T_MIN) {
+                asm volatile("mov.b32 %0, 0x7fc00000;" : "=f"(p.pxf));  // finished
+                mine = 0u;
+            } else {
+                const float4 Cc = sas_lds_f32x4(c_addr + kk * 16u);
+                const float vis = a * p.T;
+                p.ar = fmaf(Cc.x, vis, p.ar);
+                p.ag = fmaf(Cc.y, vis, p.ag);
+                p.ab = fmaf(Cc.z, vis, p.ab);
+                p.ad = fmaf(Cc.w, vis, p.ad);
+                p.T = nT;
+                if (COUNT) p.nc++;
+            }
+        }
+        __syncwarp();  // scratch is free for the next round
+    }
+}
+
 __device__ __forceinline__ void write_pixel(const SasOutputs &o, size_t pi, float r, float g, float bl, float depth, float alpha, int nc) {
     if (o.rgb) { o.rgb[3 * pi + 0] = r; o.rgb[3 * pi + 1] = g; o.rgb[3 * pi + 2] = bl; }
     if (o.alpha) o.alpha[pi] = alpha;
     if (o.depth) o.depth[pi] = depth;
     if (o.rgb_u8) { o.rgb_u8[3 * pi + 0] = to_u8(r); o.rgb_u8[3 * pi + 1] = to_u8(g); o.rgb_u8[3 * pi + 2] = to_u8(bl); }
     if (o.n_contrib) o.n_contrib[pi] = nc;
+    if (o.depth_f16) o.depth_f16[pi] = __half_as_ushort(__float2half_rn(depth));
 }
 
 __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *src) {
@@ -198,7 +356,7 @@ __constant__ int sas_variant_flags_dev = 0xff;
 // than 16): a tile with 14 reachable groups keeps 4 warps busy instead of leaving most of 8 warps waiting at the
 // batch barrier while they hold warp slots and registers.  One CTA shape, 16 resident per SM.
 template <int WARPS, int MODE, bool COUNT, bool PACKED = false>
-__global__ void __launch_bounds__(WARPS * 32, 64 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, MODE == 3 ? 10 : 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
                  const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_list, SasWork *work, int n_bg, int n_dyn,
@@ -207,12 +365,18 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
     constexpr int NT = WARPS * 32;     // threads = records per batch
     constexpr int PARTS = 8 / WARPS;   // CTAs per tile (PACKED: at most; a part beyond the tile's packed groups is skipped)
     __shared__ SasRecord stage[2][NT];
-    __shared__ unsigned s_reach[MODE == 2 ? 2 : 1][MODE == 2 ? NT : 1];
+    __shared__ unsigned s_reach[MODE >= 2 ? 2 : 1][MODE >= 2 ? NT : 1];
+    __shared__ SplitScratch s_split[MODE == 3 ? WARPS : 1];   // MODE 3: per-warp alpha rows / colours / hit queue
+    __shared__ float2 s_org[MODE == 3 ? WARPS : 1][4];        // MODE 3: centre of the first pixel of each packed group
     __shared__ unsigned s_take;
+    static_assert(MODE != 3 || (PACKED && WARPS == 4), "the split compositor is the packed 4-warp CTA");
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = tile_w * tile_h;
     const long long IT = (long long)I * T;
     unsigned staged = 0;   // in eighths of a tile's list: a list staged by the two CTAs of a tile counts once
+    // MODE 3: shared addresses of this lane's column of the alpha rows and of the colour rows of its warp's scratch
+    const unsigned split_a_addr = MODE == 3 ? sas_pin((unsigned)__cvta_generic_to_shared(&s_split[MODE == 3 ? tid >> 5 : 0].alpha[0][lane & 7])) : 0u;
+    const unsigned split_c_addr = MODE == 3 ? sas_pin((unsigned)__cvta_generic_to_shared(&s_split[MODE == 3 ? tid >> 5 : 0].col[0])) : 0u;
 
     // max_items: work items a CTA takes before it exits (0 = until the list is empty).  A bounded CTA hands its SM
     // slot back to the block scheduler, so kernels of another stream can move in while this one is still running.
@@ -287,6 +451,8 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             px = fx + 4 * cx + (gl & 3); py = fy + 2 * ry + (gl >> 2);
             warp_arg = (int)(__shfl_sync(0xffffffffu, bit, 0) | (__shfl_sync(0xffffffffu, bit, 8) << 8) |
                              (__shfl_sync(0xffffffffu, bit, 16) << 16) | (__shfl_sync(0xffffffffu, bit, 24) << 24));
+            // published by the first batch barrier below; the barrier at the top of the item loop protects its reuse
+            if (MODE == 3 && gl == 0) s_org[tid >> 5][grp] = make_float2((float)(fx + 4 * cx) + 0.5f, (float)(fy + 2 * ry) + 0.5f);
         } else {
             fx = tx * SAS_TILE_PX + (warp & 1) * 8; fy = ty * SAS_TILE_PX + (warp >> 1) * 4;  // 8 wide x 4 high
             px = fx + (grp & 1) * 4 + (gl & 3); py = fy + (grp >> 1) * 2 + (gl >> 2);
@@ -310,7 +476,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         if (NT + tid < n) gid_next = __ldg(gids + (size_t)(NT + tid) * gstride);
         for (int b = 0; b < nb; b++) {
             sas_cp_async_wait<0>();
-            if (MODE == 2) {  // this thread's record of batch b has landed: which of the tile's 32 groups can it reach
+            if (MODE >= 2) {  // this thread's record of batch b has landed: which of the tile's 32 groups can it reach
                 unsigned m = 0u;
                 if (b * NT + tid < n) {
                     const float4 A = stage[b & 1][tid].a;
@@ -331,7 +497,8 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
             if (__all_sync(0xffffffffu, p.done())) continue;  // whole warp finished: only keep feeding the pipeline
-            process_batch<MODE, COUNT, PACKED>(stage[buf], s_reach[MODE == 2 ? buf : 0], warp_arg, cnt, p, X0, Y0);
+            if (MODE == 3) process_batch_split<COUNT>(stage[buf], s_reach[buf], (unsigned)warp_arg, cnt, p, s_split[MODE == 3 ? tid >> 5 : 0], s_org[MODE == 3 ? tid >> 5 : 0], split_a_addr, split_c_addr);
+            else process_batch<MODE == 3 ? 2 : MODE, COUNT, PACKED>(stage[buf], s_reach[MODE >= 2 ? buf : 0], warp_arg, cnt, p, X0, Y0);
         }
         sas_cp_async_wait<0>();
 #undef SAS_REC_OF
@@ -391,8 +558,8 @@ __global__ void __launch_bounds__(256) ns_max_kernel(const float *__restrict__ d
 }
 
 __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, float *__restrict__ depth, const float *__restrict__ alpha,
-                                                      uint8_t *__restrict__ rgb_u8, int P, float bg0, float bg1, float bg2,
-                                                      const unsigned int *__restrict__ img_max) {
+                                                      uint8_t *__restrict__ rgb_u8, uint16_t *__restrict__ depth_f16, int P, float bg0, float bg1,
+                                                      float bg2, const unsigned int *__restrict__ img_max) {
     const int im = blockIdx.y;
     const float dmax = __uint_as_float(img_max[im]);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < P; i += gridDim.x * 256) {
@@ -404,7 +571,10 @@ __global__ void __launch_bounds__(256) ns_post_kernel(float *__restrict__ rgb, f
         const float b = fminf(fmaxf(rgb[3 * pi + 2] + om * bg2, 0.0f), 1.0f);
         rgb[3 * pi + 0] = r; rgb[3 * pi + 1] = g; rgb[3 * pi + 2] = b;
         if (rgb_u8) { rgb_u8[3 * pi + 0] = to_u8(r); rgb_u8[3 * pi + 1] = to_u8(g); rgb_u8[3 * pi + 2] = to_u8(b); }
-        if (depth && !(a > 0.0f)) depth[pi] = dmax;
+        if (depth && !(a > 0.0f)) {
+            depth[pi] = dmax;
+            if (depth_f16) depth_f16[pi] = __half_as_ushort(__float2half_rn(dmax));
+        }
     }
 }
 
@@ -451,7 +621,10 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
             const int grid = max_items > 0 ? SAS_GRID(8) : g_comp_sms * g_comp_ctas;
             if (vf & 0x200) {  // packed groups: every tile as one or two 4-warp CTAs of up to 16 packed groups each
                 const int grid4 = max_items > 0 ? SAS_GRID(4) : g_comp_sms * 16;
-                if (img_out.n_contrib) composite_kernel<4, 2, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                if (vf & 0x400) {  // split: alpha record-parallel, only the transmittance chain serial (MODE 3)
+                    if (img_out.n_contrib) composite_kernel<4, 3, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                    else composite_kernel<4, 3, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                } else if (img_out.n_contrib) composite_kernel<4, 2, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                 else composite_kernel<4, 2, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
             } else if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);
             else composite_kernel<8, 2, false><<<grid, 256, 0, st>>>(SAS_ARGS);
@@ -471,8 +644,8 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
     return cudaGetLastError();
 }
 
-cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, int I, int W, int H, float bg0,
-                               float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches) {
+cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uint8_t *rgb_u8, uint16_t *depth_f16, int I, int W, int H,
+                               float bg0, float bg1, float bg2, unsigned int *img_max, cudaStream_t st, int *n_launches) {
     const int P = W * H;
     dim3 grid(min((P + 255) / 256, 64), I);
     cudaError_t e = cudaMemsetAsync(img_max, 0, sizeof(unsigned int) * I, st);
@@ -481,7 +654,7 @@ cudaError_t sas_launch_ns_post(float *rgb, float *depth, const float *alpha, uin
         ns_max_kernel<<<grid, 256, 0, st>>>(depth, P, img_max);
         if (n_launches) *n_launches += 1;
     }
-    ns_post_kernel<<<grid, 256, 0, st>>>(rgb, depth, alpha, rgb_u8, P, bg0, bg1, bg2, img_max);
+    ns_post_kernel<<<grid, 256, 0, st>>>(rgb, depth, alpha, rgb_u8, depth_f16, P, bg0, bg1, bg2, img_max);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

@@ -185,7 +185,7 @@ __device__ unsigned long long fused_scan(int n, int *__restrict__ out, FusedShar
 __global__ void __launch_bounds__(FUSED_THREADS) scan_lists_fused_kernel(const unsigned *__restrict__ row_tile_count, const int *__restrict__ view_of_image,
                                                                          const unsigned *__restrict__ tile_dyn_mask, int C, int I, int T, int tile_w,
                                                                          int W, int H, int *__restrict__ row_tile_offset, int *__restrict__ img_tile_offset,
-                                                                         SasCounters *counters, long long capacity, SasWork *work,
+                                                                         SasCounters *counters, long long cap_src, long long cap_all, SasWork *work,
                                                                          unsigned char *__restrict__ view_tile_needed, int *__restrict__ sort_list,
                                                                          int *__restrict__ comp_list) {
     __shared__ FusedShared sh;
@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) scan_lists_fused_kernel(const u
         counters->n_isects_src = m_src;
         counters->n_isects = m_all;
         unsigned ov = 0u;
-        if (m_src > (unsigned long long)capacity) ov |= 1u;
-        if (m_all > (unsigned long long)capacity) ov |= 2u;
+        if (m_src > (unsigned long long)cap_src) ov |= 1u;
+        if (m_all > (unsigned long long)cap_all) ov |= 2u;
         if (ov) atomicOr(&counters->overflow, ov);
     }
 
@@ -279,7 +279,20 @@ __global__ void __launch_bounds__(FUSED_THREADS) scan_lists_fused_kernel(const u
     }
 }
 
+__global__ void snapshot_kernel(const SasCounters *__restrict__ counters, SasSnapRing *ring) {
+    if (threadIdx.x == 0) {
+        const unsigned long long k = ring->seq;
+        ring->slot[k & 3ull] = *counters;
+        ring->seq = k + 1ull;
+    }
+}
+
 }  // namespace
+
+cudaError_t sas_launch_snapshot(const SasCounters *counters, SasSnapRing *ring, cudaStream_t st) {
+    snapshot_kernel<<<1, 32, 0, st>>>(counters, ring);
+    return cudaGetLastError();
+}
 
 bool sas_scan_lists_fused_ok(int C, int I, int T) {
     const long long n = (long long)(C + I) * T + (long long)I * T + (long long)C * T;
@@ -288,11 +301,11 @@ bool sas_scan_lists_fused_ok(int C, int I, int T) {
 
 cudaError_t sas_launch_scan_lists_fused(const unsigned int *row_tile_count, const int *view_of_image, const unsigned int *tile_dyn_mask, int C,
                                         int I, int W, int H, int tile_w, int tile_h, int *row_tile_offset, int *img_tile_offset,
-                                        SasCounters *counters, long long capacity, SasWork *work, unsigned char *view_tile_needed,
-                                        int *sort_list, int *comp_list, cudaStream_t st, int *n_launches) {
+                                        SasCounters *counters, long long cap_src, long long cap_all, SasWork *work,
+                                        unsigned char *view_tile_needed, int *sort_list, int *comp_list, cudaStream_t st, int *n_launches) {
     scan_lists_fused_kernel<<<1, FUSED_THREADS, 0, st>>>(row_tile_count, view_of_image, tile_dyn_mask, C, I, tile_w * tile_h, tile_w, W, H,
-                                                         row_tile_offset, img_tile_offset, counters, capacity, work, view_tile_needed, sort_list,
-                                                         comp_list);
+                                                         row_tile_offset, img_tile_offset, counters, cap_src, cap_all, work, view_tile_needed,
+                                                         sort_list, comp_list);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }

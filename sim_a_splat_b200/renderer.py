@@ -28,8 +28,13 @@ def _f32c(a) -> np.ndarray:
 
 
 class SplatRenderer:
+    """One libsas handle.  `max_images` is the capacity of ONE library call; set_cameras() accepts more images than
+    that and render() then walks them in chunks (cameras are the most significant field of gsplat's sort key, so the
+    chunks reproduce the one-call images bit for bit).  `max_isects` / `max_isects_src` size the intersection buffers
+    (merged ids / sorted bucket entries); 0 = start small and let the first (checked) render grow them."""
+
     def __init__(self, scene: SplatScene, device: int = 0, max_images: int = 1, max_envs: int = 1,
-                 max_width: int = 1920, max_height: int = 1080, max_isects: int = 0):
+                 max_width: int = 1920, max_height: int = 1080, max_isects: int = 0, max_isects_src: int = 0):
         import torch
 
         if not torch.cuda.is_available():
@@ -42,7 +47,7 @@ class SplatRenderer:
         arrs = [_f32c(scene.means), _f32c(scene.quats), _f32c(scene.scales), _f32c(scene.opacities), _f32c(scene.sh),
                 np.ascontiguousarray(scene.link_id, dtype=np.int32)]
         desc = L.SceneDesc(scene.N, scene.sh_degree, scene.L, L.SAS_MEM_HOST, *[a.ctypes.data for a in arrs])
-        cfg = L.Config(int(max_images), int(max_envs), int(max_width), int(max_height), int(max_isects))
+        cfg = L.Config(int(max_images), int(max_envs), int(max_width), int(max_height), int(max_isects), int(max_isects_src))
         h = C.c_void_p()
         L.check(self._lib, None, self._lib.sas_create(C.byref(desc), C.byref(cfg), self.device, C.byref(h)))
         self._h = h
@@ -53,6 +58,10 @@ class SplatRenderer:
         # against the caller's stream with event waits on both sides.
         self._own_stream = torch.cuda.Stream(device=self.device)
         self._pinned: Dict[str, "torch.Tensor"] = {}
+        self._sized = False        # True once a checked render has sized the intersection buffers for the current cameras
+        self._cams = None          # host copy of the camera set (chunked rendering re-uploads slices of it)
+        self._pose_stage = None    # private device copy of the caller's pose tensor (foreign-stream calls)
+        self._pose_read_ev = None
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -85,16 +94,43 @@ class SplatRenderer:
             self._handoff = None
 
     # -- per-step inputs --------------------------------------------------------------------
+    def _private_copy(self, t, stream, slot: str):
+        """The library reads pose tensors asynchronously on `stream` (include/sas.h, input lifetime).  When that is not
+        the caller's current stream nothing would order the caller's next in-place update after that read, so the
+        tensor is first copied, ON THE CALLER'S STREAM, into a buffer this renderer owns; `stream` then waits for the
+        copy.  The caller may overwrite its tensor as soon as this returns.  (Calls on the caller's own stream, or on
+        the renderer's side stream with its hand-back, are ordered already.)"""
+        torch = self._torch
+        if stream is None:
+            return t
+        cur = torch.cuda.current_stream(self.device)
+        if int(stream.cuda_stream) == int(cur.cuda_stream):
+            return t
+        buf = getattr(self, slot, None)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty_like(t)
+            setattr(self, slot, buf)
+        elif self._pose_read_ev is not None:
+            cur.wait_event(self._pose_read_ev)   # the previous read of the private buffer (issued steps ago) has run
+        buf.copy_(t)                             # on the caller's stream
+        stream.wait_stream(cur)
+        return buf
+
+    def _after_private_read(self, stream) -> None:
+        if stream is not None and int(stream.cuda_stream) != int(self._torch.cuda.current_stream(self.device).cuda_stream):
+            self._pose_read_ev = stream.record_event()
+
     def set_link_poses(self, poses, stream=None) -> None:
         """poses [E,L,12] (rot row-major | pos): numpy (host) or a CUDA float32 tensor (device)."""
         if self.L == 0:
             return
         torch = self._torch
         if isinstance(poses, torch.Tensor) and poses.is_cuda:
-            p = poses.contiguous().float()
+            p = self._private_copy(poses.contiguous().float(), stream, "_pose_stage")
             E = p.numel() // (self.L * 12)
             code = self._lib.sas_set_link_poses(self._h, C.c_void_p(p.data_ptr()), E, L.SAS_MEM_DEVICE, self._stream(stream))
             self._keep_poses = p
+            self._after_private_read(stream)
         else:
             p = _f32c(poses.cpu().numpy() if isinstance(poses, torch.Tensor) else poses).reshape(-1, self.L, 12)
             code = self._lib.sas_set_link_poses(self._h, p.ctypes.data, p.shape[0], L.SAS_MEM_HOST, self._stream(stream))
@@ -120,10 +156,11 @@ class SplatRenderer:
         drive the link groups (manipulator_env.py:377-390), numpy (host) or a CUDA float64 tensor."""
         torch = self._torch
         if isinstance(body_wxyz_xyz, torch.Tensor) and body_wxyz_xyz.is_cuda:
-            b = body_wxyz_xyz.contiguous().double()
+            b = self._private_copy(body_wxyz_xyz.contiguous().double(), stream, "_body_stage")
             code = self._lib.sas_set_link_poses_from_bodies(self._h, C.c_void_p(b.data_ptr()), b.numel() // (self.L * 7), L.SAS_MEM_DEVICE,
                                                             self._stream(stream))
             self._keep_bodies = b
+            self._after_private_read(stream)
         else:
             b = np.ascontiguousarray(body_wxyz_xyz, dtype=np.float64).reshape(-1, self.L, 7)
             code = self._lib.sas_set_link_poses_from_bodies(self._h, b.ctypes.data, b.shape[0], L.SAS_MEM_HOST, self._stream(stream))
@@ -148,7 +185,8 @@ class SplatRenderer:
         return xyz, valid.bool()
 
     def set_cameras(self, viewmats, Ks, width: int, height: int, env_of_image: Optional[Sequence[int]] = None, stream=None) -> None:
-        """viewmats [I,4,4] world->camera (OpenCV axes), Ks [I,3,3] or [3,3]; host arrays."""
+        """viewmats [I,4,4] world->camera (OpenCV axes), Ks [I,3,3] or [3,3]; host arrays.  I may exceed the handle's
+        max_images: render() then goes through the images in chunks of at most max_images (one library call each)."""
         vm = _f32c(viewmats).reshape(-1, 16)
         I = vm.shape[0]
         K = _f32c(Ks).reshape(-1, 9)
@@ -158,19 +196,34 @@ class SplatRenderer:
         if env_of_image is not None:
             env = np.ascontiguousarray(env_of_image, dtype=np.int32)
             assert env.shape == (I,)
-        code = self._lib.sas_set_cameras(self._h, vm.ctypes.data, K.ctypes.data, env.ctypes.data if env is not None else None,
-                                         I, int(width), int(height), self._stream(stream))
+        self._cams = (vm, K, env)
+        if (I, int(width), int(height)) != (self.I, self.W, self.H):
+            self._sized = False   # another batch shape: the next unchecked render re-sizes the intersection buffers first
+        self.I, self.W, self.H = I, int(width), int(height)
+        self._chunk = None if I <= self.max_images else self.max_images   # images per library call in chunked mode
+        if self._chunk is None:
+            self._upload_cameras(0, I, stream)
+
+    def _upload_cameras(self, i0: int, i1: int, stream=None) -> None:
+        vm, K, env = self._cams
+        e = env[i0:i1] if env is not None else None
+        code = self._lib.sas_set_cameras(self._h, vm[i0:i1].ctypes.data, K[i0:i1].ctypes.data, e.ctypes.data if e is not None else None,
+                                         i1 - i0, self.W, self.H, self._stream(stream))
         L.check(self._lib, self._h, code)
         self._handback()
-        self.I, self.W, self.H = I, int(width), int(height)
 
     # -- render -----------------------------------------------------------------------------
+    _SHAPES = {"rgb": (3, "float32"), "depth": (0, "float32"), "alpha": (0, "float32"), "rgb_u8": (3, "uint8"),
+               "n_contrib": (0, "int32"), "depth_f16": (0, "float16")}
+
+    def _shape_dtype(self, name: str):
+        ch, dt = self._SHAPES[name]
+        shape = (self.I, self.H, self.W, 3) if ch else (self.I, self.H, self.W)
+        return shape, getattr(self._torch, dt)
+
     def _alloc(self, name: str, to_host: bool, slot: int = 0):
         torch = self._torch
-        I, H, W = self.I, self.H, self.W
-        shape, dt = {"rgb": ((I, H, W, 3), torch.float32), "depth": ((I, H, W), torch.float32),
-                     "alpha": ((I, H, W), torch.float32), "rgb_u8": ((I, H, W, 3), torch.uint8),
-                     "n_contrib": ((I, H, W), torch.int32)}[name]
+        shape, dt = self._shape_dtype(name)
         if to_host:
             t = self._pinned.get((name, slot))
             if t is None or tuple(t.shape) != shape:
@@ -179,66 +232,183 @@ class SplatRenderer:
             return t
         return torch.empty(shape, dtype=dt, device=f"cuda:{self.device}")
 
+    def _alloc_packed(self, names: Sequence[str], slot: int = 0) -> dict:
+        """Pinned host tensors for `names`, all views of ONE pinned block cut up by sas_packed_layout: the library
+        then brings the whole observation back in a single D2H copy."""
+        torch = self._torch
+        key = ("packed", tuple(names), slot, self.I, self.H, self.W)
+        hit = self._pinned.get(key)
+        if hit is not None:
+            return hit
+        want = 0
+        for n in names:
+            want |= 1 << L.OUT_ORDER.index(n)
+        offs = (C.c_size_t * 6)()
+        total = C.c_size_t()
+        code = self._lib.sas_packed_layout(self.I, self.W, self.H, want, offs, C.byref(total))
+        if code != L.SAS_OK:
+            raise L.SasError(code, "sas_packed_layout: bad shape or output mask")
+        block = torch.empty(int(total.value), dtype=torch.uint8, pin_memory=True)
+        bufs = {"_block": block}
+        for n in names:
+            shape, dt = self._shape_dtype(n)
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            o = int(offs[L.OUT_ORDER.index(n)])
+            bufs[n] = block[o:o + nbytes].view(dt).view(shape)
+        for k in [k for k in self._pinned if isinstance(k, tuple) and k[0] == "packed" and k[2] == slot and k[1] == tuple(names) and k != key]:
+            del self._pinned[k]   # a block of another shape for the same outputs
+        self._pinned[key] = bufs
+        return bufs
+
+    def _outputs_struct(self, bufs: dict, mem: int, nerfstudio_post: bool, background, offset_images: int = 0) -> "L.Outputs":
+        o = L.Outputs()
+        o.mem = mem
+        o.nerfstudio_post = 1 if nerfstudio_post else 0
+        o.background = (C.c_float * 3)(*[float(b) for b in background])
+        for n in L.OUT_ORDER:
+            t = bufs.get(n)
+            if t is None:
+                setattr(o, n, None)
+            else:
+                per_image = t[0].numel() * t.element_size() if t.shape[0] else 0
+                setattr(o, n, C.c_void_p(t.data_ptr() + offset_images * per_image))
+        return o
+
+    _ISECT_CAP = 0x7ffffff0   # int32 offsets inside the library
+
+    def _render_checked(self, o, st) -> bool:
+        """One library call; on overflow grow the intersection buffers (from the device counters) and render again.
+        Returns False if the frame cannot fit the library's int32 offsets (the caller then halves the chunk)."""
+        for attempt in range(3):
+            try:
+                L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
+            except L.SasError as e:
+                if e.code != -4:
+                    raise
+            s = self.stats()
+            if not s["overflow"]:
+                return True
+            if s["n_isects"] > self._ISECT_CAP or s["n_isects_src"] > self._ISECT_CAP:
+                return False
+            need_src = int(s["n_isects_src"] * 1.25) + 1024 if s["n_isects_src"] > s["cap_isects_src"] else 0
+            need_all = int(s["n_isects"] * 1.25) + 1024 if s["n_isects"] > s["cap_isects"] else 0
+            L.check(self._lib, self._h, self._lib.sas_reserve_isects2(self._h, min(need_src, self._ISECT_CAP), min(need_all, self._ISECT_CAP)))
+        raise L.SasError(-4, "intersection buffers still overflow after growing them twice")
+
     def render(self, outputs: Iterable[str] = ("rgb", "depth", "alpha"), background=(0.0, 0.0, 0.0),
                nerfstudio_post: bool = False, to_host: bool = False, out: Optional[dict] = None, stream=None,
                check: bool = True) -> dict:
         """Render every image set by set_cameras.  Returns {name: torch tensor}: CUDA tensors, or (to_host=True)
         pinned host tensors filled by a D2H copy inside the call (which then synchronises the stream).
         check=True reads the device counters afterwards (a sync) and transparently grows the intersection
-        buffers and re-renders if they overflowed."""
+        buffers and re-renders if they overflowed; check=False never synchronises -- overflow then surfaces as an
+        exception from a host-output render, or through poll_overflow()."""
         if self.I == 0:
             raise RuntimeError("set_cameras has not been called")
         names = list(outputs)
+        if self._chunk is not None:
+            return self._render_chunked(names, background, nerfstudio_post, to_host, out, check)
         bufs = dict(out) if out else {}
-        for n in names:
-            if n not in bufs:
-                bufs[n] = self._alloc(n, to_host)
-        o = L.Outputs()
-        o.mem = L.SAS_MEM_HOST if to_host else L.SAS_MEM_DEVICE
-        o.nerfstudio_post = 1 if nerfstudio_post else 0
-        o.background = (C.c_float * 3)(*[float(b) for b in background])
-        for n in ("rgb", "depth", "alpha", "rgb_u8", "n_contrib"):
-            setattr(o, n, C.c_void_p(bufs[n].data_ptr()) if n in bufs else None)
+        missing = [n for n in names if n not in bufs]
+        if missing:
+            if to_host and not out:
+                bufs.update(self._alloc_packed(names))
+            else:
+                for n in missing:
+                    bufs[n] = self._alloc(n, to_host)
+        o = self._outputs_struct({n: bufs[n] for n in names}, L.SAS_MEM_HOST if to_host else L.SAS_MEM_DEVICE, nerfstudio_post, background)
         st = self._stream(stream)
-        L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
         if check:
-            s = self.stats()
-            if s["overflow"]:
-                L.check(self._lib, self._h, self._lib.sas_reserve_isects(self._h, int(s["n_isects"] * 1.25) + 1024))
-                L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
-                if self.stats()["overflow"]:
-                    raise L.SasError(-4, "intersection buffers overflowed twice")
+            if not self._render_checked(o, st):
+                raise L.SasError(-4, "this camera set needs more than 2^31 intersections in one call: create the renderer with a "
+                                     "smaller max_images so that render() walks the images in chunks")
+            self._sized = True
+        else:
+            L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), st))
         self._handback()
         return {n: bufs[n] for n in names}
+
+    def _render_chunked(self, names, background, nerfstudio_post, to_host, out, check: bool = True) -> dict:
+        """More images than one library call takes (or than fit its int32 intersection offsets): the images are
+        rendered max_images at a time into slices of the full output tensors.  The image index is the most
+        significant field of gsplat's sort key, so every chunk is exactly the corresponding part of the one-call
+        result.  A chunk that still overflows the offsets is halved.  check=False (after a checked pass has sized the
+        buffers and settled the chunk size) issues the calls without reading the counters back."""
+        torch = self._torch
+        dev = dict(out) if (out and not to_host) else {}
+        for n in names:
+            if n not in dev:
+                dev[n] = self._alloc(n, False)
+        i0, step = 0, int(self._chunk)
+        while i0 < self.I:
+            i1 = min(self.I, i0 + step)
+            self._upload_cameras(i0, i1)
+            o = self._outputs_struct({n: dev[n] for n in names}, L.SAS_MEM_DEVICE, nerfstudio_post, background, offset_images=i0)
+            if not check:
+                L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), self._stream(None)))
+            elif not self._render_checked(o, self._stream(None)):
+                if step == 1:
+                    raise L.SasError(-4, "a single image needs more than 2^31 intersections")
+                step = max(1, step // 2)
+                self._chunk = step   # remembered: later (unchecked) passes use the size that fits
+                continue
+            self._handback()
+            i0 = i1
+        if not to_host:
+            return {n: dev[n] for n in names}
+        host = dict(out) if out else {}
+        for n in names:
+            if n not in host:
+                host[n] = self._alloc(n, True)
+            host[n].copy_(dev[n], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {n: host[n] for n in names}
+
+    def _size_buffers_once(self, names, background, nerfstudio_post, stream) -> None:
+        """Unchecked (asynchronous) renders cannot grow the intersection buffers themselves, so the first one after
+        set_cameras is preceded by ONE checked device render with the same poses, which sizes the buffers (plus 50 %
+        head-room for the steps to come).  Later overflows are reported, never silent: wait() raises for host
+        outputs, poll_overflow() tells for device outputs."""
+        if self._sized:
+            return
+        if self._chunk is not None:
+            raise RuntimeError("asynchronous rendering is not available in chunked mode (more images than max_images)")
+        dev = {n: self._alloc(n, False) for n in names}
+        o = self._outputs_struct(dev, L.SAS_MEM_DEVICE, nerfstudio_post, background)
+        if not self._render_checked(o, self._stream(stream)):
+            raise L.SasError(-4, "this camera set needs more than 2^31 intersections in one call")
+        s = self.stats()
+        L.check(self._lib, self._h, self._lib.sas_reserve_isects2(self._h, min(int(s["n_isects_src"] * 1.5) + 4096, self._ISECT_CAP),
+                                                                  min(int(s["n_isects"] * 1.5) + 4096, self._ISECT_CAP)))
+        self._handback()
+        self._sized = True
 
     def render_async(self, outputs: Iterable[str] = ("rgb_u8", "depth"), background=(0.0, 0.0, 0.0),
                      nerfstudio_post: bool = False, stream=None) -> int:
         """Issue a render into pinned host buffers WITHOUT waiting for it (sas_outputs.mem = SAS_MEM_HOST_ASYNC): the
-        D2H copies run on the library's copy stream out of one of two alternating staging sets, so the transfer of
-        step k overlaps the render of step k+1.  Returns a ticket for wait().  At most two renders may be outstanding
-        (issue k+1, then wait(k)); the tensors wait(k) returned are reused by render k+2.  No overflow check: size
-        max_isects beforehand (stats()['overflow'] after a render tells)."""
+        D2H copy (ONE, the outputs share a pinned block) runs on the library's copy stream out of one of two
+        alternating staging sets, so the transfer of step k overlaps the render of step k+1.  Returns a ticket for
+        wait().  At most two renders may be outstanding (issue k+1, then wait(k)); the tensors wait(k) returned are
+        reused by render k+2.  The first call sizes the intersection buffers with one checked render; if a later step
+        overflows them, wait() raises (the frame is incomplete) -- reserve_isects() and carry on."""
         if self.I == 0:
             raise RuntimeError("set_cameras has not been called")
         seq = getattr(self, "_async_seq", 0)
         names = list(outputs)
-        bufs = {n: self._alloc(n, True, slot=seq & 1) for n in names}
-        o = L.Outputs()
-        o.mem = L.SAS_MEM_HOST_ASYNC
-        o.nerfstudio_post = 1 if nerfstudio_post else 0
-        o.background = (C.c_float * 3)(*[float(b) for b in background])
-        for n in ("rgb", "depth", "alpha", "rgb_u8", "n_contrib"):
-            setattr(o, n, C.c_void_p(bufs[n].data_ptr()) if n in bufs else None)
+        self._size_buffers_once(names, background, nerfstudio_post, stream)
+        bufs = self._alloc_packed(names, slot=seq & 1)
+        o = self._outputs_struct({n: bufs[n] for n in names}, L.SAS_MEM_HOST_ASYNC, nerfstudio_post, background)
         L.check(self._lib, self._h, self._lib.sas_render(self._h, C.byref(o), self._stream(stream)))
         self._handback()
         if not hasattr(self, "_async_bufs"):
             self._async_bufs = [None, None]
-        self._async_bufs[seq & 1] = bufs
+        self._async_bufs[seq & 1] = {n: bufs[n] for n in names}
         self._async_seq = seq + 1
         return seq
 
     def wait(self, ticket: Optional[int] = None) -> dict:
-        """Block until the host buffers of render_async ticket (default: the latest) are complete; returns them."""
+        """Block until the host buffers of render_async ticket (default: the latest) are complete; returns them.
+        Raises SasError(-4) if that frame overflowed the intersection buffers (it is incomplete)."""
         seq = getattr(self, "_async_seq", 0)
         if ticket is None:
             ticket = seq - 1
@@ -251,8 +421,19 @@ class SplatRenderer:
             raise RuntimeError("wait(): the buffers of this ticket have been reused by a later render_async")
         return self._async_bufs[ticket & 1]
 
-    def reserve_isects(self, n: int) -> None:
-        L.check(self._lib, self._h, self._lib.sas_reserve_isects(self._h, int(n)))
+    def reserve_isects(self, n: int, n_src: Optional[int] = None) -> None:
+        """Capacity for n merged intersections and n_src sorted bucket entries (default: n)."""
+        L.check(self._lib, self._h, self._lib.sas_reserve_isects2(self._h, int(n if n_src is None else n_src), int(n)))
+
+    def poll_overflow(self, stream=None) -> Optional[dict]:
+        """Did one of the last (up to 4) renders since the previous poll overflow the intersection buffers?  Synchronises
+        the stream.  None, or {'n_isects_src': ..., 'n_isects': ...} = the capacities that would have sufficed."""
+        ns, na = C.c_longlong(), C.c_longlong()
+        code = self._lib.sas_poll_overflow(self._h, C.byref(ns), C.byref(na), self._stream(stream))
+        self._handback()
+        if code < 0:
+            L.check(self._lib, self._h, code)
+        return {"n_isects_src": int(ns.value), "n_isects": int(na.value)} if code == 1 else None
 
     def stats(self) -> dict:
         s = L.Stats()
@@ -409,9 +590,23 @@ class PipelinedSplatRenderer:
         bufs = self._dev_out.get((k, names))
         if bufs is None or any(tuple(b.shape[:3]) != (r.I, r.H, r.W) for b in bufs.values()):
             bufs = self._dev_out[(k, names)] = {n: r._alloc(n, False) for n in names}
+        r._size_buffers_once(list(names), background, nerfstudio_post, s)   # first use: one checked render sizes the buffers
         r.render(names, background=background, nerfstudio_post=nerfstudio_post, out=bufs, stream=s, check=False)
         self._seq += 1
         return bufs
+
+    def poll_overflow(self) -> None:
+        """Synchronises every handle's stream and raises SasError(-4) if one of their recent device-output renders
+        overflowed its intersection buffers (those frames were incomplete); grows the buffers for the steps to come."""
+        bad = None
+        for r, s in zip(self.renderers, self.streams):
+            need = r.poll_overflow(stream=s)
+            if need:
+                r.reserve_isects(int(need["n_isects"] * 1.5) + 4096, int(need["n_isects_src"] * 1.5) + 4096)
+                bad = need
+        if bad:
+            raise L.SasError(-4, f"a recent render overflowed the intersection buffers (needed {bad}); they have been grown, "
+                                 "the affected frames were incomplete")
 
     def join(self) -> None:
         """Order the caller's current stream after every step issued so far."""

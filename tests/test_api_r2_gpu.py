@@ -1,0 +1,170 @@
+"""Round-2 boundary features, through the C ABI on the GPU: one-copy packed host outputs and the fp16 depth output,
+chunked rendering of more images than one library call takes, overflow that is reported instead of silently
+truncating asynchronous renders, env-index validation, the input lifetime of pose tensors handed to a renderer that
+works on its own stream, separate capacities for sorted bucket entries and merged ids."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from sim_a_splat_b200 import _lib as L
+from sim_a_splat_b200 import scene as S
+from sim_a_splat_b200.renderer import PipelinedSplatRenderer, SplatRenderer
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene():
+    return S.make_synthetic_scene(9000, 3, seed=77, link_counts=(400, 250, 150))
+
+
+def _setup(r, sc, E, W, H, n_cams=2, seed=5):
+    cams = S.ring_cameras(n_cams, (0, 0, 0), seed=seed)
+    vms = np.tile(cams, (E, 1, 1))
+    env = np.repeat(np.arange(E, dtype=np.int32), n_cams)
+    poses = S.random_link_poses(E, sc.L, seed=900)
+    r.set_link_poses(poses)
+    r.set_cameras(vms, S.fov_intrinsics(W, H), W, H, env)
+    return vms, env, poses
+
+
+def test_packed_host_outputs_one_block_and_fp16_depth():
+    sc = _scene()
+    W, H, E = 80, 64, 3
+    r = SplatRenderer(sc, max_images=2 * E, max_envs=E, max_width=W, max_height=H)
+    _setup(r, sc, E, W, H)
+    names = ("rgb_u8", "depth_f16", "depth", "alpha", "rgb", "n_contrib")
+    dev = {k: v.cpu() for k, v in r.render(names).items()}
+    host = r.render(names, to_host=True)
+    blk = r._alloc_packed(list(names))["_block"]
+    lo, hi = blk.data_ptr(), blk.data_ptr() + blk.numel()
+    for k in names:
+        assert host[k].is_pinned() and lo <= host[k].data_ptr() < hi, k       # views of ONE pinned block
+        assert host[k].data_ptr() % 256 == lo % 256, k                         # the library's 256-byte aligned layout
+        assert torch.equal(host[k], dev[k]), k
+    # fp16 depth = round-to-nearest-even of the f32 expected depth (what torch's .half() does)
+    assert host["depth_f16"].dtype == torch.float16
+    assert torch.equal(host["depth_f16"].view(torch.int16), dev["depth"].half().view(torch.int16))
+    # a subset, and host buffers that are NOT one block (per-output copies) give the same bytes
+    sub = r.render(("rgb_u8", "depth"), to_host=True)
+    assert torch.equal(sub["rgb_u8"], dev["rgb_u8"]) and torch.equal(sub["depth"], dev["depth"])
+    loose = {"rgb_u8": torch.empty_like(dev["rgb_u8"]).pin_memory(), "depth": torch.empty_like(dev["depth"]).pin_memory()}
+    got = r.render(("rgb_u8", "depth"), to_host=True, out=loose)
+    assert torch.equal(got["rgb_u8"], dev["rgb_u8"]) and torch.equal(got["depth"], dev["depth"])
+    # nerfstudio post-processing keeps the fp16 copy in step with the f32 depth it rewrites where alpha == 0
+    ns = r.render(("depth", "depth_f16"), nerfstudio_post=True, background=(0.1, 0.2, 0.3))
+    assert torch.equal(ns["depth_f16"].view(torch.int16), ns["depth"].half().view(torch.int16))
+    r.close()
+
+
+def test_async_host_outputs_match_blocking():
+    sc = _scene()
+    W, H, E = 64, 48, 4
+    r = SplatRenderer(sc, max_images=2 * E, max_envs=E, max_width=W, max_height=H)
+    _setup(r, sc, E, W, H)
+    ref = {k: v.cpu() for k, v in r.render(("rgb_u8", "depth_f16")).items()}
+    tickets = [r.render_async(("rgb_u8", "depth_f16")) for _ in range(2)]
+    for t in tickets:
+        got = r.wait(t)
+        assert torch.equal(got["rgb_u8"], ref["rgb_u8"]) and torch.equal(got["depth_f16"].view(torch.int16), ref["depth_f16"].view(torch.int16))
+    r.close()
+
+
+def test_chunked_render_reproduces_one_call_bit_for_bit():
+    sc = _scene()
+    W, H, E = 96, 80, 5
+    names = ("rgb", "depth", "alpha", "rgb_u8", "n_contrib")
+    full = SplatRenderer(sc, max_images=2 * E, max_envs=E, max_width=W, max_height=H)
+    _setup(full, sc, E, W, H)
+    a = {k: v.clone() for k, v in full.render(names).items()}
+    full.close()
+    ch = SplatRenderer(sc, max_images=3, max_envs=E, max_width=W, max_height=H)   # 10 images in calls of 3, 3, 3, 1
+    _setup(ch, sc, E, W, H)
+    b = ch.render(names)
+    for k in names:
+        assert torch.equal(a[k], b[k]), k
+    h = ch.render(("rgb_u8", "depth"), to_host=True)
+    assert torch.equal(h["rgb_u8"], a["rgb_u8"].cpu()) and torch.equal(h["depth"], a["depth"].cpu())
+    with pytest.raises(RuntimeError):
+        ch.render_async(("rgb_u8",))
+    ch.close()
+
+
+def test_overflow_is_reported_not_silent():
+    sc = _scene()
+    W, H, E = 96, 96, 4
+    r = SplatRenderer(sc, max_images=2 * E, max_envs=E, max_width=W, max_height=H, max_isects=2048, max_isects_src=1024)
+    _setup(r, sc, E, W, H)
+    st0 = r.stats()
+    assert st0["cap_isects"] == 2048 and st0["cap_isects_src"] == 1024
+    # (a) unchecked device render: nothing raises at once, poll_overflow() tells and names the capacities that suffice
+    r.render(("rgb",), check=False)
+    need = r.poll_overflow()
+    assert need is not None and need["n_isects"] > 2048 and need["n_isects_src"] > 1024
+    assert r.poll_overflow() is None                       # reported once
+    # (b) blocking host render: SAS_ECAPACITY from the library itself
+    o = r._outputs_struct({"rgb_u8": r._alloc("rgb_u8", True)}, L.SAS_MEM_HOST, False, (0, 0, 0))
+    code = r._lib.sas_render(r._h, C.byref(o), r._stream(None))
+    r._handback()
+    assert code == -4 and b"INCOMPLETE" in r._lib.sas_last_error(r._h)
+    # (c) asynchronous host render whose buffers are too small: wait() raises
+    r._sized = True                                        # pretend an earlier step had sized the buffers
+    t = r.render_async(("rgb_u8",))
+    with pytest.raises(L.SasError) as ei:
+        r.wait(t)
+    assert ei.value.code == -4
+    # (d) the normal path: the first asynchronous render sizes the buffers with one checked render, separately
+    r._sized = False
+    got = r.wait(r.render_async(("rgb_u8",)))
+    st = r.stats()
+    assert st["overflow"] == 0 and st["cap_isects"] >= st["n_isects"] and st["cap_isects_src"] >= st["n_isects_src"]
+    assert st["cap_isects_src"] < st["cap_isects"]         # shared views: far fewer sorted entries than merged ids
+    ref = r.render(("rgb_u8",))["rgb_u8"].cpu()
+    assert torch.equal(got["rgb_u8"], ref)
+    r.close()
+
+
+def test_env_index_beyond_uploaded_poses_is_rejected():
+    sc = _scene()
+    W, H = 48, 48
+    r = SplatRenderer(sc, max_images=4, max_envs=4, max_width=W, max_height=H)
+    cams = S.ring_cameras(1, (0, 0, 0), seed=3)
+    r.set_link_poses(S.random_link_poses(2, sc.L, seed=1))                  # poses of envs 0 and 1 only
+    r.set_cameras(np.repeat(cams, 3, axis=0), S.fov_intrinsics(W, H), W, H, np.array([0, 1, 3], np.int32))
+    with pytest.raises(L.SasError) as ei:
+        r.render(("rgb",))
+    assert ei.value.code == -5
+    r.set_link_poses(S.random_link_poses(4, sc.L, seed=1))
+    r.render(("rgb",))
+    r.close()
+
+
+def test_pose_tensor_may_be_overwritten_right_after_the_call():
+    """a renderer that works on its own stream reads the caller's pose tensor asynchronously; the Python
+    layer takes a private copy on the caller's stream, so an in-place update for the next step cannot race it."""
+    sc = _scene()
+    W, H, E = 64, 64, 8
+    pr = PipelinedSplatRenderer(sc, depth=2, max_images=E, max_envs=E, max_width=W, max_height=H)
+    cams = S.ring_cameras(1, (0, 0, 0), seed=9)
+    pr.set_cameras(np.repeat(cams, E, axis=0), S.fov_intrinsics(W, H), W, H, np.arange(E))
+    pa, pb = (torch.from_numpy(S.random_link_poses(E, sc.L, seed=s)).cuda() for s in (11, 12))
+    ref = SplatRenderer(sc, max_images=E, max_envs=E, max_width=W, max_height=H)
+    ref.set_cameras(np.repeat(cams, E, axis=0), S.fov_intrinsics(W, H), W, H, np.arange(E))
+    want = []
+    for p in (pa, pb):
+        ref.set_link_poses(p)
+        want.append(ref.render(("rgb",))["rgb"].clone())
+    buf = pa.clone()
+    big = torch.empty(64 << 20, device="cuda")
+    outs = []
+    for k in range(6):
+        src = pa if k % 2 == 0 else pb
+        buf.copy_(src)
+        big.normal_()                      # keeps the caller's stream busy so the handle's stream runs behind it
+        pr.set_link_poses(buf)
+        buf.zero_()                        # the caller reuses its tensor immediately
+        outs.append(pr.render(("rgb",))["rgb"])
+        pr.join()
+        assert torch.equal(outs[-1], want[k % 2]), k
+    pr.close(); ref.close()

@@ -53,32 +53,28 @@ def time_config(name, sc, vms, K, W, H, poses, env, steps, max_isects=0):
 
 
 def main():
+    from sim_a_splat_b200 import workloads as WL
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--n5", type=int, default=6_000_000)
     ap.add_argument("--cams5", type=int, default=8)
+    ap.add_argument("--only", type=str, default="")
     a = ap.parse_args()
-    # configs[0]: one 640x480 frame of the pusht scene (the reference's CPU-runnable case)
-    sc = S.make_reference_like_scene("robots-scene-v2", 3, 101, with_tblock=True)
-    cen = sc.means[sc.link_id >= 0].mean(0)
-    time_config("configs[0] tblock pusht scene 640x480 x1", sc, S.ring_cameras(1, cen, 7), S.fov_intrinsics(640, 480), 640, 480,
-                S.random_link_poses(1, sc.L, 1000), np.zeros(1, np.int32), a.steps)
-    # configs[2]: xarm, 4 cameras x 1280x720
-    sc = S.make_reference_like_scene("robots-scene-v2", 3, 103)
-    cen = sc.means[sc.link_id >= 0].mean(0)
-    time_config("configs[2] xarm 4 cameras x 1280x720", sc, S.ring_cameras(4, cen, 9), S.fov_intrinsics(1280, 720), 1280, 720,
-                S.random_link_poses(1, 7, 2000), np.zeros(4, np.int32), a.steps)
-    # configs[3]: the 256-env x 2-camera shard one of 8 GPUs renders
-    sc = S.make_reference_like_scene("divar113vhw", 3, 104)
-    cen = sc.means[sc.link_id >= 0].mean(0)
-    E = 256
-    time_config("configs[3] divar113vhw shard: 256 envs x 2 cameras x 224x224", sc, np.tile(S.ring_cameras(2, cen, 10), (E, 1, 1)),
-                S.fov_intrinsics(224, 224), 224, 224, S.random_link_poses(E, 6, 3000), np.repeat(np.arange(E, dtype=np.int32), 2), a.steps,
-                max_isects=120_000_000)
-    # configs[4]: synthetic N-Gaussian SH-3 scene at 1920x1080, cameras in chunks
-    sc = S.make_synthetic_scene(a.n5, 3, seed=105)
-    time_config(f"configs[4] synthetic {a.n5} Gaussians SH3 1920x1080 x{a.cams5} cameras (one chunk of the 64)", sc,
-                S.ring_cameras(a.cams5, (0, 0, 0), seed=14), S.fov_intrinsics(1920, 1080), 1920, 1080, None, None, max(a.steps // 4, 3))
+    only = [int(x) for x in a.only.split(",")] if a.only else [0, 2, 3, 4]
+    if 0 in only:
+        sc, vms, K, W, H, poses, env = WL.config0_single_frame()
+        time_config("configs[0] tblock pusht scene 640x480 x1", sc, vms, K, W, H, poses, env, a.steps)
+    if 2 in only:
+        sc, vms, K, W, H, poses, env = WL.config2_xarm()
+        time_config("configs[2] xarm 4 cameras x 1280x720", sc, vms, K, W, H, poses, env, a.steps)
+    if 3 in only:  # the 256-env x 2-camera shard one of 8 GPUs renders
+        sc, vms, K, W, H, poses, env = WL.config3_divar(2048, 0, 256)
+        time_config("configs[3] divar113vhw shard: 256 envs x 2 cameras x 224x224", sc, vms, K, W, H, poses, env, a.steps, max_isects=120_000_000)
+    if 4 in only:
+        sc, vms, K, W, H, poses, env = WL.config4_stress(a.cams5, a.n5)
+        time_config(f"configs[4] synthetic {a.n5} Gaussians SH3 1920x1080 x{a.cams5} cameras (one chunk of the 64)", sc, vms, K, W, H,
+                    None, None, max(a.steps // 4, 3))
 
 
 if __name__ == "__main__":
