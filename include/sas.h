@@ -77,7 +77,14 @@ typedef struct {
     int64_t max_isects;     /* M cap: merged (image,tile,gaussian) intersections per render call; 0 = auto */
     int64_t max_isects_src; /* cap of the bucket entries actually emitted and sorted (background once per VIEW +
                                links per image; with shared cameras several times smaller than M); 0 = max_isects */
+    int32_t radius_rule;    /* SAS_RADIUS_TORCH (0, the pinned default): radii = ceil(3.33 sqrt(cov2d)), gsplat's torch
+                               implementation; SAS_RADIUS_CUDA_1_5 (1): gsplat 1.5's CUDA rule, the extend also shrinks with
+                               the opacity, min(3.33, sqrt(2 ln(255 o))), and o < 1/255 is culled.  Fewer intersections, the
+                               same images (a pixel outside either box has alpha < 1/255) */
+    int32_t reserved_;
 } sas_config;
+#define SAS_RADIUS_TORCH 0
+#define SAS_RADIUS_CUDA_1_5 1
 
 /* Output buffers of one render call.  Any pointer may be NULL (not produced). */
 typedef struct {
@@ -171,6 +178,31 @@ int sas_set_pose_model(sas_renderer *r, const sas_pose_model *model);
  * rot = Ri Rm Rfk^T Ri^T, pos = -rot ti - s Ri Rm Rfk^T tfk + s Ri (p + body_offset) + ti in fp64 and stores the
  * fp32 [n_envs, L, 12] block sas_set_link_poses would have been given. */
 int sas_set_link_poses_from_bodies(sas_renderer *r, const double *body_wxyz_xyz, int n_envs, int mem, void *stream);
+
+/* Pose source without Drake.  Replaces: ManipulatorSimEnv._generate_draw_msg's body poses
+ * (manipulator_env.py:377-390, Drake SceneGraph) for the robot bodies, computed from joint angles by forward kinematics
+ * over the URDF's joint tree ON THE DEVICE -- the chain urchin evaluates for the reference's capture-time frames
+ * (splat_handler.py:158-163, :197).  HOST pointers; copied.  Joints in parent-before-child order; link frame 0 is the
+ * root link (posed at `base`), frame j+1 the child link of joint j. */
+typedef struct {
+    int32_t n_joints;           /* J <= 48 */
+    int32_t n_actuated;         /* A: columns of the joint-angle array */
+    int32_t n_bodies;           /* B <= L: link groups 0..B-1 are driven by these bodies, the rest are free bodies */
+    const int32_t *parent;      /* [J] frame index of the joint's parent link */
+    const int32_t *type;        /* [J] 0 fixed, 1 revolute / continuous, 2 prismatic */
+    const int32_t *qindex;      /* [J] column of q (a mimic joint: the column of the joint it follows), -1 = fixed at 0 */
+    const double *mimic;        /* [J,2] q_joint = multiplier * q[qindex] + offset; (1, 0) for ordinary joints */
+    const double *origin;       /* [J,16] row-major 4x4 <origin> of the joint */
+    const double *axis;         /* [J,3] */
+    const double *base;         /* [16] row-major 4x4 world pose of the root link; NULL = identity */
+    const int32_t *body_frame;  /* [B] frame index of body b */
+} sas_fk_model;
+int sas_set_fk_model(sas_renderer *r, const sas_fk_model *model);
+
+/* joint angles [n_envs, A] fp64 -> body poses -> link poses (needs sas_set_pose_model as well).  free_bodies
+ * [n_envs, L - B, 7] fp64 (quaternion wxyz | position) are the poses of the link groups that are not robot bodies (the
+ * T-block); NULL = identity.  Both arrays live in `mem`; the input lifetime rule of sas_set_link_poses applies. */
+int sas_set_link_poses_from_joints(sas_renderer *r, const double *q, int n_envs, const double *free_bodies, int mem, void *stream);
 
 /* Replaces: the pinhole unprojection of GaussianSplat.generate_RGBD_point_cloud (nerfstudio_utils.py:441-452):
  * xyz[i,v,u] = ((u-cx) d/fx, (v-cy) d/fy, d) in the camera frame (OpenCV axes), valid = d < max_depth.

@@ -43,6 +43,10 @@ def _lib():
         lib.orc_render.restype = C.POINTER(_Frame)
         lib.orc_render.argtypes = [C.POINTER(_Scene), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.orc_render2.restype = C.POINTER(_Frame)
+        lib.orc_render2.argtypes = lib.orc_render.argtypes + [C.c_int]
+        lib.orc_extend_export.restype = C.c_float
+        lib.orc_extend_export.argtypes = [C.c_int, C.c_float]
         lib.orc_frame_free.argtypes = [C.POINTER(_Frame)]
         lib.orc_frame_free.restype = None
         lib.orc_exp_neg_export.restype = C.c_float
@@ -88,8 +92,11 @@ def camera_origin(viewmats: np.ndarray) -> np.ndarray:
     return (-np.einsum("nji,nj->ni", vm[:, :3, :3], vm[:, :3, 3])).astype(np.float32)
 
 
+RADIUS_RULES = {"torch": 0, "cuda_1_5": 1}
+
+
 def render(scene: dict, viewmats, Ks, W: int, H: int, link_poses=None, env_of_image=None,
-           bg=(0.0, 0.0, 0.0), stages: int = 3, keep=None) -> OracleFrame:
+           bg=(0.0, 0.0, 0.0), stages: int = 3, keep=None, radius_rule: str = "torch") -> OracleFrame:
     """scene: dict(means[N,3], quats[N,4] wxyz, scales[N,3] linear, opacities[N] linear,
     sh[N,K,3], link_id[N] int32 (-1 background), L).  link_poses [E,L,12] fp32."""
     lib = _lib()
@@ -118,8 +125,8 @@ def render(scene: dict, viewmats, Ks, W: int, H: int, link_poses=None, env_of_im
     bgv = f32(bg)
     sc = _Scene(N, deg, L, means.ctypes.data, quats.ctypes.data, scales.ctypes.data, opac.ctypes.data,
                 sh.ctypes.data, link_id.ctypes.data)
-    fp = lib.orc_render(C.byref(sc), lp.ctypes.data if lp is not None else None, E, vm.ctypes.data,
-                        Kc.ctypes.data, campos.ctypes.data, env.ctypes.data, I, W, H, bgv.ctypes.data, stages)
+    fp = lib.orc_render2(C.byref(sc), lp.ctypes.data if lp is not None else None, E, vm.ctypes.data,
+                         Kc.ctypes.data, campos.ctypes.data, env.ctypes.data, I, W, H, bgv.ctypes.data, stages, RADIUS_RULES[radius_rule])
     f = fp.contents
     M = int(f.M)
     th, tw = f.tile_h, f.tile_w

@@ -30,7 +30,8 @@
  * separately): every float operation is an individually rounded IEEE-754
  * binary32 operation in exactly the order written here (compile with
  * -ffp-contract=off, no -ffast-math); a fused multiply-add happens only where
- * fmaf() is written.  sqrtf and '/' are correctly rounded.  No libm
+ * fmaf() is written -- which since round 2 includes every 3-term inner product
+ * of the projection (dot3 / aff3 below) and the SH dot product.  sqrtf and '/' are correctly rounded.  No libm
  * transcendental is used on any path that feeds an integer decision: exp() in
  * the compositor is the explicit polynomial orc_exp_neg() below.
  *
@@ -116,10 +117,20 @@ static inline float orc_exp_neg(float x) {
 }
 float orc_exp_neg_export(float x) { return orc_exp_neg(x); }
 
+/* a0 b0 + a1 b1 + a2 b2 as ONE product and TWO fused multiply-adds, in this order; aff3 adds the products onto t.
+ * Every 3-term inner product of the projection is written through these two (round 2: gsplat's own CUDA contracts
+ * these sums to FMAs as well; the unfused form doubled the instruction count of the projection kernel). */
+static inline float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+}
+static inline float aff3(float a0, float a1, float a2, float b0, float b1, float b2, float t) {
+    return fmaf(a2, b2, fmaf(a1, b1, fmaf(a0, b0, t)));
+}
+
 /* gsplat _quat_to_rotmat on F.normalize(q): row-major R[9]. */
 static inline void quat_to_rotmat(const float *q, float *R) {
     float w = q[0], x = q[1], y = q[2], z = q[3];
-    float n = sqrtf(((w * w + x * x) + y * y) + z * z);
+    float n = sqrtf(fmaf(z, z, fmaf(y, y, fmaf(x, x, w * w))));
     n = fmaxf(n, 1e-12f);
     float inv = 1.0f / n;
     w = w * inv; x = x * inv; y = y * inv; z = z * inv;
@@ -130,17 +141,17 @@ static inline void quat_to_rotmat(const float *q, float *R) {
     R[6] = 2.0f * (xz - wy);        R[7] = 2.0f * (yz + wx);        R[8] = 1.0f - 2.0f * (x2 + y2);
 }
 
-/* C = A*B, 3x3 row-major, each entry (a0*b0 + a1*b1) + a2*b2. */
+/* C = A*B, 3x3 row-major, each entry dot3(row of A, column of B). */
 static inline void mat3_mul(const float *A, const float *B, float *C) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++)
-            C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+            C[3 * i + j] = dot3(A[3 * i], A[3 * i + 1], A[3 * i + 2], B[j], B[3 + j], B[6 + j]);
 }
 /* C = A*B^T */
 static inline void mat3_mul_bt(const float *A, const float *B, float *C) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++)
-            C[3 * i + j] = (A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1]) + A[3 * i + 2] * B[3 * j + 2];
+            C[3 * i + j] = dot3(A[3 * i], A[3 * i + 1], A[3 * i + 2], B[3 * j], B[3 * j + 1], B[3 * j + 2]);
 }
 
 /* gsplat _eval_sh_bases_fast (Sloan), K=(deg+1)^2 basis values for unit dir. */
@@ -171,7 +182,22 @@ static inline void sh_bases(int deg, float x, float y, float z, float *b) {
 /* S0-S4 for one (image, gaussian). viewmat row-major 4x4 world->cam (OpenCV
  * axes, +z forward), K row-major 3x3, campos = camera origin in world (passed
  * in so both sides use the same fp32 value), pose = [rot(9) | pos(3)] or NULL. */
-static void project_one(const orc_scene *s, int g, const float *pose, const float *vm, const float *Kc,
+/* Radius rule.  0 (pinned default): gsplat's torch implementation, radii = ceil(3.33 sqrt(cov2d)).
+ * 1 ("cuda_1_5"): gsplat 1.5's CUDA projection also shrinks the extend with the opacity -- a Gaussian whose peak alpha
+ * is o reaches alpha >= 1/255 only within sqrt(2 ln(255 o)) sigma -- extend = min(3.33, sqrt(2 ln(o / (1/255)))) and
+ * culls o < 1/255 [RECALLED].  The factor depends on the Gaussian alone; it is evaluated once per Gaussian in double
+ * precision and rounded to float (the product does the same on the host at scene upload, so both sides multiply by
+ * the same float).  Images are unaffected: a pixel outside either box has alpha < 1/255. */
+static float orc_extend(int radius_rule, float opacity) {
+    if (radius_rule != 1) return ORC_EXTEND;
+    if (opacity < ORC_ALPHA_MIN) return 0.0f;
+    double e = sqrt(2.0 * log((double)opacity / (double)ORC_ALPHA_MIN));
+    float ef = (float)e;
+    return ef < ORC_EXTEND ? ef : ORC_EXTEND;
+}
+float orc_extend_export(int radius_rule, float opacity) { return orc_extend(radius_rule, opacity); }
+
+static void project_one(const orc_scene *s, int g, float extend, const float *pose, const float *vm, const float *Kc,
                         const float *campos, int W, int H, int tile_w, int tile_h,
                         int32_t *radii, float *mean2d, float *depth, float *conic, float *color,
                         int32_t *ntiles, int32_t *rect) {
@@ -184,18 +210,18 @@ static void project_one(const orc_scene *s, int g, const float *pose, const floa
     quat_to_rotmat(s->quats + 4 * g, Rg);
     float mx = mu[0], my = mu[1], mz = mu[2];
     if (pose) { /* S0: mu' = rot*mu + pos ; R' = rot*R(q)  (splat_handler.py:283-288 semantics) */
-        float tx = ((pose[0] * mx + pose[1] * my) + pose[2] * mz) + pose[9];
-        float ty = ((pose[3] * mx + pose[4] * my) + pose[5] * mz) + pose[10];
-        float tz = ((pose[6] * mx + pose[7] * my) + pose[8] * mz) + pose[11];
+        float tx = aff3(pose[0], pose[1], pose[2], mx, my, mz, pose[9]);
+        float ty = aff3(pose[3], pose[4], pose[5], mx, my, mz, pose[10]);
+        float tz = aff3(pose[6], pose[7], pose[8], mx, my, mz, pose[11]);
         mx = tx; my = ty; mz = tz;
         mat3_mul(pose, Rg, R);
     } else {
         memcpy(R, Rg, sizeof(R));
     }
     /* world -> camera mean */
-    float cx_ = ((vm[0] * mx + vm[1] * my) + vm[2] * mz) + vm[3];
-    float cy_ = ((vm[4] * mx + vm[5] * my) + vm[6] * mz) + vm[7];
-    float cz_ = ((vm[8] * mx + vm[9] * my) + vm[10] * mz) + vm[11];
+    float cx_ = aff3(vm[0], vm[1], vm[2], mx, my, mz, vm[3]);
+    float cy_ = aff3(vm[4], vm[5], vm[6], mx, my, mz, vm[7]);
+    float cz_ = aff3(vm[8], vm[9], vm[10], mx, my, mz, vm[11]);
     if (cz_ < ORC_NEAR || cz_ > ORC_FAR) return;
 
     /* S1: Sigma = (R S)(R S)^T */
@@ -221,19 +247,19 @@ static void project_one(const orc_scene *s, int g, const float *pose, const floa
     float txc = cz_ * fminf(lim_x_pos, fmaxf(-lim_x_neg, cx_ * rz));
     float tyc = cz_ * fminf(lim_y_pos, fmaxf(-lim_y_neg, cy_ * rz));
     float ja = fx * rz, jb = -(fx * txc) * rz2, jc = fy * rz, jd = -(fy * tyc) * rz2;
-    float jc00 = ja * Cc[0] + jb * Cc[6], jc01 = ja * Cc[1] + jb * Cc[7], jc02 = ja * Cc[2] + jb * Cc[8];
-    float jc11 = jc * Cc[4] + jd * Cc[7], jc12 = jc * Cc[5] + jd * Cc[8];
-    float a = jc00 * ja + jc02 * jb;
-    float b = jc01 * jc + jc02 * jd;
-    float c = jc11 * jc + jc12 * jd;
-    float m2x = (fx * cx_) * rz + pcx;
-    float m2y = (fy * cy_) * rz + pcy;
+    float jc00 = fmaf(jb, Cc[6], ja * Cc[0]), jc01 = fmaf(jb, Cc[7], ja * Cc[1]), jc02 = fmaf(jb, Cc[8], ja * Cc[2]);
+    float jc11 = fmaf(jd, Cc[7], jc * Cc[4]), jc12 = fmaf(jd, Cc[8], jc * Cc[5]);
+    float a = fmaf(jc02, jb, jc00 * ja);
+    float b = fmaf(jc02, jd, jc01 * jc);
+    float c = fmaf(jc12, jd, jc11 * jc);
+    float m2x = fmaf(fx * cx_, rz, pcx);
+    float m2y = fmaf(fy * cy_, rz, pcy);
     a = a + ORC_EPS2D; c = c + ORC_EPS2D;
-    float det = a * c - b * b;
+    float det = fmaf(a, c, -(b * b));
     if (!(det > 0.0f)) return;
     det = fmaxf(det, 1e-10f);
-    float rx = ceilf(ORC_EXTEND * sqrtf(a));
-    float ry = ceilf(ORC_EXTEND * sqrtf(c));
+    float rx = ceilf(extend * sqrtf(a));
+    float ry = ceilf(extend * sqrtf(c));
     if (rx <= 0.0f && ry <= 0.0f) return;
     if (m2x + rx <= 0.0f || m2x - rx >= (float)W || m2y + ry <= 0.0f || m2y - ry >= (float)H) return;
 
@@ -245,12 +271,12 @@ static void project_one(const orc_scene *s, int g, const float *pose, const floa
     /* S3: SH colour; view direction in the link's rest frame: rot^T (mu' - campos) */
     float dx = mx - campos[0], dy = my - campos[1], dz = mz - campos[2];
     if (pose) {
-        float ux = (pose[0] * dx + pose[3] * dy) + pose[6] * dz;
-        float uy = (pose[1] * dx + pose[4] * dy) + pose[7] * dz;
-        float uz = (pose[2] * dx + pose[5] * dy) + pose[8] * dz;
+        float ux = dot3(pose[0], pose[3], pose[6], dx, dy, dz);
+        float uy = dot3(pose[1], pose[4], pose[7], dx, dy, dz);
+        float uz = dot3(pose[2], pose[5], pose[8], dx, dy, dz);
         dx = ux; dy = uy; dz = uz;
     }
-    float dn = sqrtf((dx * dx + dy * dy) + dz * dz);
+    float dn = sqrtf(dot3(dx, dy, dz, dx, dy, dz));
     dn = fmaxf(dn, 1e-12f);
     float dinv = 1.0f / dn;
     dx = dx * dinv; dy = dy * dinv; dz = dz * dinv;
@@ -260,7 +286,7 @@ static void project_one(const orc_scene *s, int g, const float *pose, const floa
     const float *co = s->sh + (size_t)g * Kn * 3;
     for (int ch = 0; ch < 3; ch++) {
         float acc = bas[0] * co[ch];
-        for (int k = 1; k < Kn; k++) acc = acc + bas[k] * co[3 * k + ch];
+        for (int k = 1; k < Kn; k++) acc = fmaf(bas[k], co[3 * k + ch], acc);
         color[ch] = fmaxf(acc + 0.5f, 0.0f);
     }
 
@@ -307,9 +333,17 @@ void orc_frame_free(orc_frame *f) {
  * 3 = + compositing (S8).  keep_dense = 0 skips nothing (all intermediates are
  * always kept; the caller frees with orc_frame_free).
  */
+orc_frame *orc_render2(const orc_scene *s, const float *link_poses, int E, const float *viewmats,
+                       const float *Ks, const float *campos, const int32_t *env_of_image, int I,
+                       int W, int H, const float *bg, int stages, int radius_rule);
 orc_frame *orc_render(const orc_scene *s, const float *link_poses, int E, const float *viewmats,
                       const float *Ks, const float *campos, const int32_t *env_of_image, int I,
                       int W, int H, const float *bg, int stages) {
+    return orc_render2(s, link_poses, E, viewmats, Ks, campos, env_of_image, I, W, H, bg, stages, 0);
+}
+orc_frame *orc_render2(const orc_scene *s, const float *link_poses, int E, const float *viewmats,
+                       const float *Ks, const float *campos, const int32_t *env_of_image, int I,
+                       int W, int H, const float *bg, int stages, int radius_rule) {
     orc_frame *f = (orc_frame *)calloc(1, sizeof(orc_frame));
     int N = s->N;
     int tile_w = (W + ORC_TILE - 1) / ORC_TILE, tile_h = (H + ORC_TILE - 1) / ORC_TILE;
@@ -332,7 +366,7 @@ orc_frame *orc_render(const orc_scene *s, const float *link_poses, int E, const 
             size_t ig = (size_t)im * N + g;
             int l = s->link_id ? s->link_id[g] : -1;
             const float *pose = (l >= 0 && link_poses) ? link_poses + ((size_t)env_of_image[im] * s->L + l) * 12 : NULL;
-            project_one(s, g, pose, viewmats + 16 * im, Ks + 9 * im, campos + 3 * im, W, H, tile_w, tile_h,
+            project_one(s, g, orc_extend(radius_rule, s->opacities[g]), pose, viewmats + 16 * im, Ks + 9 * im, campos + 3 * im, W, H, tile_w, tile_h,
                         f->radii + 2 * ig, f->means2d + 2 * ig, f->depths + ig, f->conics + 3 * ig,
                         f->colors + 3 * ig, f->tiles_per_gauss + ig, f->tile_rect + 4 * ig);
         }

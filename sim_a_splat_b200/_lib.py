@@ -27,7 +27,7 @@ EXPORTS = [
     "sas_create", "sas_destroy", "sas_set_link_poses", "sas_set_cameras", "sas_render", "sas_reserve_isects",
     "sas_set_pose_model", "sas_set_link_poses_from_bodies", "sas_unproject_depth", "sas_wait_outputs",
     "sas_get_stats", "sas_set_stage_timing", "sas_get_stage_ms", "sas_debug_fetch", "sas_last_launch_count", "sas_last_error", "sas_version",
-    "sas_reserve_isects2", "sas_packed_layout", "sas_poll_overflow",
+    "sas_reserve_isects2", "sas_packed_layout", "sas_poll_overflow", "sas_set_fk_model", "sas_set_link_poses_from_joints",
 ]
 
 # bit k of a SAS_OUT_* mask <-> output name (the order of sas_packed_layout)
@@ -42,7 +42,7 @@ class SceneDesc(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("max_images", C.c_int32), ("max_envs", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
-                ("max_isects", C.c_int64), ("max_isects_src", C.c_int64)]
+                ("max_isects", C.c_int64), ("max_isects_src", C.c_int64), ("radius_rule", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Outputs(C.Structure):
@@ -62,6 +62,12 @@ class Stats(C.Structure):
 class PoseModel(C.Structure):
     _fields_ = [("n_links", C.c_int32), ("scale", C.c_double), ("Ri", C.c_double * 9), ("ti", C.c_double * 3),
                 ("fk_R", C.c_void_p), ("fk_t", C.c_void_p), ("body_offset", C.c_void_p)]
+
+
+class FkModel(C.Structure):
+    _fields_ = [("n_joints", C.c_int32), ("n_actuated", C.c_int32), ("n_bodies", C.c_int32), ("parent", C.c_void_p), ("type", C.c_void_p),
+                ("qindex", C.c_void_p), ("mimic", C.c_void_p), ("origin", C.c_void_p), ("axis", C.c_void_p), ("base", C.c_void_p),
+                ("body_frame", C.c_void_p)]
 
 
 class SasError(RuntimeError):
@@ -98,6 +104,10 @@ def load(build_if_missing: bool = True):
     lib.sas_set_pose_model.restype = C.c_int
     lib.sas_set_link_poses_from_bodies.argtypes = [P, P, C.c_int, C.c_int, P]
     lib.sas_set_link_poses_from_bodies.restype = C.c_int
+    lib.sas_set_fk_model.argtypes = [P, C.POINTER(FkModel)]
+    lib.sas_set_fk_model.restype = C.c_int
+    lib.sas_set_link_poses_from_joints.argtypes = [P, P, C.c_int, P, C.c_int, P]
+    lib.sas_set_link_poses_from_joints.restype = C.c_int
     lib.sas_unproject_depth.argtypes = [P, P, C.c_int, C.c_int, C.c_int, P, C.c_float, P, P, C.c_int, P]
     lib.sas_unproject_depth.restype = C.c_int
     lib.sas_set_cameras.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, P]

@@ -7,6 +7,7 @@
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: stage ranges for nsys / ncu --nvtx filtering
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +33,7 @@ struct sas_renderer {
     // scene (SoA)
     float4 *mean_op = nullptr, *quat = nullptr, *scale_link = nullptr;
     float *sh_planes = nullptr;
+    float *extend = nullptr;             // per-Gaussian radius extend (radius_rule = cuda_1_5), else null
     // per-call state
     float *link_poses = nullptr;
     int n_envs = 0;
@@ -49,6 +51,9 @@ struct sas_renderer {
     SasPoseModel pose_model{};            // device pointers inside; pose_model.L == 0: not set
     double *fk_dev = nullptr;             // [L,15]: fk_R, fk_t, body_offset
     DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
+    SasFkModel fk_model{};                // device pointers inside; fk_model.J == 0: not set
+    int fk_actuated = 0;
+    DevBuf fk_blob, fk_q, fk_extra;
     cudaStream_t aux[SAS_SORT_CLASSES - 1] = {};      // side streams: the bucket-sort size classes run concurrently
     cudaEvent_t fork_ev[SAS_SORT_CLASSES] = {};       // [0] fork, [1..] joins
     cudaEvent_t scan_ev[3] = {};                      // fork / two joins of the scan + work-list chains
@@ -255,6 +260,7 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(sas_sort_init(n_sms));
     SAS_CUDA_C(sas_composite_init(n_sms));
     SAS_CUDA_C(sas_bin_init());
+    SAS_CUDA_C(sas_project_init());
 
     // bring the scene to the host if needed, pack SoA, upload
     std::vector<float> h_means((size_t)N * 3), h_quats((size_t)N * 4), h_scales((size_t)N * 3), h_op(N), h_sh((size_t)N * K * 3);
@@ -296,6 +302,24 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     SAS_CUDA_C(cudaMemcpy(r->quat, p_quat.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
     SAS_CUDA_C(cudaMemcpy(r->scale_link, p_scale.data(), sizeof(float4) * N, cudaMemcpyHostToDevice));
     SAS_CUDA_C(cudaMemcpy(r->sh_planes, p_sh.data(), sizeof(float) * p_sh.size(), cudaMemcpyHostToDevice));
+    if (cfg->radius_rule == SAS_RADIUS_CUDA_1_5) {
+        // the same double-precision expression, rounded once to float, as oracle/splat_oracle.c:orc_extend
+        std::vector<float> ext(N);
+        const float amin = 1.0f / 255.0f;
+        for (int g = 0; g < N; g++) {
+            float e = 0.0f;
+            if (!(h_op[g] < amin)) {
+                e = (float)sqrt(2.0 * log((double)h_op[g] / (double)amin));
+                if (!(e < 3.33f)) e = 3.33f;
+            }
+            ext[g] = e;
+        }
+        SAS_CUDA_C(cudaMalloc(&r->extend, sizeof(float) * N));
+        SAS_CUDA_C(cudaMemcpy(r->extend, ext.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    } else if (cfg->radius_rule != SAS_RADIUS_TORCH) {
+        r->err = "sas_create: unknown radius_rule";
+        return bail(SAS_EINVAL);
+    }
 
     const int maxE = cfg->max_envs > 0 ? cfg->max_envs : 1;
     if (r->L > 0) {
@@ -333,7 +357,7 @@ void sas_destroy(sas_renderer *r) {
     cudaSetDevice(r->device);
     cudaDeviceSynchronize();
     cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
-    cudaFree(r->fk_dev);
+    cudaFree(r->fk_dev); cudaFree(r->extend);
     cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters); cudaFree(r->snap);
     if (r->h_snap) cudaFreeHost(r->h_snap);
     if (r->stage_host) cudaFreeHost(r->stage_host);
@@ -357,7 +381,8 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_alpha[0], &r->o_pack[0], &r->o_pack[1],
-                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid};
+                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid,
+                      &r->fk_blob, &r->fk_q, &r->fk_extra};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
 }
@@ -427,6 +452,79 @@ int sas_set_link_poses_from_bodies(sas_renderer *r, const double *body, int n_en
         d_body = (const double *)r->body_dev.p;
     }
     SAS_CUDA(r, sas_launch_link_poses(d_body, r->pose_model, n_envs, r->link_poses, st));
+    r->n_envs = n_envs;
+    return SAS_OK;
+}
+
+int sas_set_fk_model(sas_renderer *r, const sas_fk_model *model) {
+    if (!r || !model) return SAS_EINVAL;
+    const int J = model->n_joints, B = model->n_bodies;
+    if (J <= 0 || J > sas_fk_max_joints() || B <= 0 || B > r->L || model->n_actuated <= 0 || !model->parent || !model->type || !model->qindex ||
+        !model->mimic || !model->origin || !model->axis || !model->body_frame)
+        return fail(r, SAS_EINVAL, "sas_set_fk_model: 0 < n_joints <= 48, 0 < n_bodies <= the scene's link count, and all arrays must be given");
+    for (int j = 0; j < J; j++)
+        if (model->parent[j] < 0 || model->parent[j] > j || model->qindex[j] >= model->n_actuated || model->type[j] < 0 || model->type[j] > 2)
+            return fail(r, SAS_EINVAL, "sas_set_fk_model: joints must be in parent-before-child order with valid type / qindex");
+    for (int b = 0; b < B; b++)
+        if (model->body_frame[b] < 0 || model->body_frame[b] > J) return fail(r, SAS_EINVAL, "sas_set_fk_model: body_frame out of range");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    // one blob: ints (parent, type, qindex | body_frame) then doubles (mimic, origin 12 per joint, axis)
+    const size_t n_int = (size_t)3 * J + B, int_bytes = (n_int * 4 + 7) & ~(size_t)7, n_dbl = (size_t)J * (2 + 12 + 3);
+    std::vector<unsigned char> blob(int_bytes + n_dbl * 8);
+    int *pi = reinterpret_cast<int *>(blob.data());
+    double *pd = reinterpret_cast<double *>(blob.data() + int_bytes);
+    for (int j = 0; j < J; j++) { pi[j] = model->parent[j]; pi[J + j] = model->type[j]; pi[2 * J + j] = model->qindex[j]; }
+    for (int b = 0; b < B; b++) pi[3 * J + b] = model->body_frame[b];
+    for (int j = 0; j < J; j++) {
+        pd[2 * j] = model->mimic[2 * j]; pd[2 * j + 1] = model->mimic[2 * j + 1];
+        double *o = pd + 2 * J + 12 * j;
+        const double *M = model->origin + 16 * j;
+        for (int i = 0; i < 3; i++) { for (int k = 0; k < 3; k++) o[3 * i + k] = M[4 * i + k]; o[9 + i] = M[4 * i + 3]; }
+        for (int k = 0; k < 3; k++) pd[2 * J + 12 * J + 3 * j + k] = model->axis[3 * j + k];
+    }
+    int rc;
+    if ((rc = ensure(r, r->fk_blob, blob.size()))) return rc;
+    SAS_CUDA(r, cudaMemcpy(r->fk_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    SasFkModel &m = r->fk_model;
+    const unsigned char *d = (const unsigned char *)r->fk_blob.p;
+    m.J = J; m.B = B;
+    m.parent = (const int *)d; m.type = m.parent + J; m.qindex = m.parent + 2 * J; m.body_frame = m.parent + 3 * J;
+    m.mimic = (const double *)(d + int_bytes); m.origin = m.mimic + 2 * J; m.axis = m.origin + 12 * J;
+    for (int i = 0; i < 3; i++) {
+        for (int k = 0; k < 3; k++) m.base[3 * i + k] = model->base ? model->base[4 * i + k] : (i == k ? 1.0 : 0.0);
+        m.base[9 + i] = model->base ? model->base[4 * i + 3] : 0.0;
+    }
+    r->fk_actuated = model->n_actuated;
+    return SAS_OK;
+}
+
+int sas_set_link_poses_from_joints(sas_renderer *r, const double *q, int n_envs, const double *free_bodies, int mem, void *stream) {
+    if (!r) return SAS_EINVAL;
+    if (r->fk_model.J == 0 || r->pose_model.L == 0)
+        return fail(r, SAS_ESTATE, "sas_set_link_poses_from_joints: sas_set_fk_model and sas_set_pose_model must be called first");
+    if (!q || n_envs <= 0) return fail(r, SAS_EINVAL, "sas_set_link_poses_from_joints: null joint angles or n_envs <= 0");
+    const int maxE = r->cfg.max_envs > 0 ? r->cfg.max_envs : 1;
+    if (n_envs > maxE) return fail(r, SAS_ECAPACITY, "sas_set_link_poses_from_joints: n_envs exceeds max_envs");
+    SAS_CUDA(r, cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const double *d_q = q, *d_extra = free_bodies;
+    const int n_free = r->L - r->fk_model.B;
+    if (mem != SAS_MEM_DEVICE) {
+        const size_t qb = sizeof(double) * (size_t)n_envs * r->fk_actuated;
+        if ((rc = ensure(r, r->fk_q, qb))) return rc;
+        SAS_CUDA(r, cudaMemcpyAsync(r->fk_q.p, q, qb, cudaMemcpyHostToDevice, st));
+        d_q = (const double *)r->fk_q.p;
+        if (free_bodies && n_free > 0) {
+            const size_t eb = sizeof(double) * 7 * (size_t)n_envs * n_free;
+            if ((rc = ensure(r, r->fk_extra, eb))) return rc;
+            SAS_CUDA(r, cudaMemcpyAsync(r->fk_extra.p, free_bodies, eb, cudaMemcpyHostToDevice, st));
+            d_extra = (const double *)r->fk_extra.p;
+        }
+    }
+    if ((rc = ensure(r, r->body_dev, sizeof(double) * 7 * (size_t)n_envs * r->L))) return rc;
+    SAS_CUDA(r, sas_launch_fk(d_q, r->fk_actuated, r->fk_model, n_envs, n_free > 0 ? d_extra : nullptr, r->L, (double *)r->body_dev.p, st));
+    SAS_CUDA(r, sas_launch_link_poses((const double *)r->body_dev.p, r->pose_model, n_envs, r->link_poses, st));
     r->n_envs = n_envs;
     return SAS_OK;
 }
@@ -586,7 +684,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
         if (sp.n <= 0) continue;
         SAS_CUDA(r, sas_launch_project(r->mean_op, r->quat, r->scale_link, r->sh_planes, r->n_pad, r->sh_degree,
                                        r->L > 0 ? r->link_poses : nullptr, r->L, r->row_cams, sp, W, H, tw, th, rec, bins, (uint2 *)r->radii.p, rcount,
-                                       sp.row0 == C ? dyn_mask : nullptr, r->counters, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
+                                       sp.row0 == C ? dyn_mask : nullptr, r->counters, r->extend, (two_spans && sp.row0 == 0) ? r->aux[2] : st));
         launches += 1;
     }
     if (two_spans) SAS_CUDA(r, join_span());

@@ -196,6 +196,8 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //   bit 9  compositor: the groups link Gaussians can reach packed four per warp, a tile = one or two CTAs of 4 warps
 //   bit 10 compositor (with bit 9): "split" -- alpha evaluated record-parallel (lane = hit, 8 pixels each), only the
 //          transmittance chain serial per pixel (sas_composite.cu MODE 3)
+//   bit 11 compositor (with bit 9): bulk-async staging -- one 48-byte cp.async.bulk per record completing on an mbarrier
+//          with expect_tx (UBLKCP / SYNCS in SASS) instead of three 16-byte cp.async (LDGSTS) + wait_group
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -220,6 +222,21 @@ struct SasPoseModel {
     const double *fk_R, *fk_t, *offset;
 };
 
+// URDF joint tree for the device forward kinematics (sas_pose.cu fk_kernel); all pointers are device pointers.
+struct SasFkModel {
+    int J, B;                 // joints (parent-before-child order), bodies produced
+    const int *parent;        // [J] link frame the joint hangs from (0 = root link, j + 1 = child frame of joint j)
+    const int *type;          // [J] 0 fixed, 1 revolute / continuous, 2 prismatic
+    const int *qindex;        // [J] column of q that drives the joint (a mimic joint: its source's column), -1 = none
+    const int *body_frame;    // [B] link frame of output body b
+    const double *mimic;      // [J,2] multiplier, offset (1, 0 for ordinary joints)
+    const double *origin;     // [J,12] joint origin: rotation row-major (9) | translation (3)
+    const double *axis;       // [J,3] unit axis
+    double base[12];          // world pose of the root link
+};
+cudaError_t sas_launch_fk(const double *q, int A, const SasFkModel &m, int E, const double *extra, int L, double *body, cudaStream_t st);
+int sas_fk_max_joints();
+
 // Launchers (each returns the cudaError_t of the launch).
 cudaError_t sas_launch_link_poses(const double *body, const SasPoseModel &m, int E, float *out, cudaStream_t st);
 cudaError_t sas_launch_unproject(const float *depth, int I, int W, int H, float fx, float fy, float cx, float cy, float max_depth, float *xyz,
@@ -240,8 +257,9 @@ cudaError_t sas_launch_project(const float4 *mean_op, const float4 *quat, const 
                                int n_pad, int sh_degree, const float *link_poses, int L, const SasCamera *row_cams,
                                SasRowSpan span, int W, int H, int tile_w, int tile_h, SasRecord *rec, uint2 *bins,
                                uint2 *radii_out, unsigned int *row_tile_count, unsigned int *tile_dyn_mask, SasCounters *counters,
-                               cudaStream_t st);
+                               const float *extend /*per-Gaussian radius extend or null = 3.33*/, cudaStream_t st);
 cudaError_t sas_bin_init();
+cudaError_t sas_project_init();
 cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_of_image, int C, int T, int *offsets,
                             unsigned int *block_sums, SasCounters *counters, long long capacity, cudaStream_t st, int *n_launches);
 cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,

@@ -337,6 +337,31 @@ __device__ __forceinline__ void write_pixel(const SasOutputs &o, size_t pi, floa
     if (o.depth_f16) o.depth_f16[pi] = __half_as_ushort(__float2half_rn(depth));
 }
 
+// ---- bulk-async staging (SAS_VARIANT bit 11): one 48-byte cp.async.bulk per record, completing on an mbarrier with
+// expect_tx, instead of three 16-byte cp.async (LDGSTS) + wait_group.  TMA *tensor* copies do not apply (the records
+// of a tile list are a data-dependent gather), the 1-D bulk copy does: UBLKCP + SYNCS in SASS.
+__device__ __forceinline__ void sas_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sas_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sas_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SAS_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra SAS_WAIT_%=;\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sas_bulk_copy48(void *smem_dst, const void *gmem_src, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 48, [%2];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void stage_record(SasRecord *dst, const SasRecord *src) {
     sas_cp_async16(&dst->a, &src->a);
     sas_cp_async16(&dst->b, &src->b);
@@ -355,7 +380,7 @@ __constant__ int sas_variant_flags_dev = 0xff;
 // four per warp, in sas_group_bit order, and the tile becomes ONE CTA of 4 warps (up to 16 packed groups) or TWO (more
 // than 16): a tile with 14 reachable groups keeps 4 warps busy instead of leaving most of 8 warps waiting at the
 // batch barrier while they hold warp slots and registers.  One CTA shape, 16 resident per SM.
-template <int WARPS, int MODE, bool COUNT, bool PACKED = false>
+template <int WARPS, int MODE, bool COUNT, bool PACKED = false, bool BULK = false>
 __global__ void __launch_bounds__(WARPS * 32, MODE == 3 ? 10 : 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
@@ -369,6 +394,16 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
     __shared__ SplitScratch s_split[MODE == 3 ? WARPS : 1];   // MODE 3: per-warp alpha rows / colours / hit queue
     __shared__ float2 s_org[MODE == 3 ? WARPS : 1][4];        // MODE 3: centre of the first pixel of each packed group
     __shared__ unsigned s_take;
+    __shared__ __align__(8) unsigned long long s_mbar[2];     // BULK: one transaction barrier per stage buffer
+    unsigned mbar_parity = 0u;                                // BULK: bit s = parity of the next completion of s_mbar[s]
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            sas_mbar_init(&s_mbar[0], 1u);
+            sas_mbar_init(&s_mbar[1], 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     static_assert(MODE != 3 || (PACKED && WARPS == 4), "the split compositor is the packed 4-warp CTA");
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = tile_w * tile_h;
@@ -471,11 +506,21 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         // ---- batches: prologue puts batch 0 in flight and the id of batch 1 in a register ----
         const int nb = (n + NT - 1) / NT;
         int gid_next = 0;
-        if (tid < n) stage_record(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)));
-        sas_cp_async_commit();
+        if (BULK) {
+            if (tid == 0 && n > 0) sas_mbar_expect_tx(&s_mbar[0], (unsigned)min(NT, n) * 48u);
+            if (tid < n) sas_bulk_copy48(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)), &s_mbar[0]);
+        } else {
+            if (tid < n) stage_record(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)));
+            sas_cp_async_commit();
+        }
         if (NT + tid < n) gid_next = __ldg(gids + (size_t)(NT + tid) * gstride);
         for (int b = 0; b < nb; b++) {
-            sas_cp_async_wait<0>();
+            if (BULK) {   // every thread waits for the whole batch (all bytes landed: the barrier's transaction count is zero)
+                sas_mbar_wait(&s_mbar[b & 1], (mbar_parity >> (b & 1)) & 1u);
+                mbar_parity ^= 1u << (b & 1);
+            } else {
+                sas_cp_async_wait<0>();
+            }
             if (MODE >= 2) {  // this thread's record of batch b has landed: which of the tile's 32 groups can it reach
                 unsigned m = 0u;
                 if (b * NT + tid < n) {
@@ -491,8 +536,14 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             const int buf = b & 1;
             {  // batch b+1 -> other buffer; id of batch b+2 -> register
                 const int e1 = (b + 1) * NT + tid;
-                if (e1 < n) stage_record(&stage[buf ^ 1][tid], SAS_REC_OF(gid_next));
-                sas_cp_async_commit();
+                if (BULK) {
+                    const int c1 = min(NT, n - (b + 1) * NT);
+                    if (tid == 0 && c1 > 0) sas_mbar_expect_tx(&s_mbar[buf ^ 1], (unsigned)c1 * 48u);
+                    if (e1 < n) sas_bulk_copy48(&stage[buf ^ 1][tid], SAS_REC_OF(gid_next), &s_mbar[buf ^ 1]);
+                } else {
+                    if (e1 < n) stage_record(&stage[buf ^ 1][tid], SAS_REC_OF(gid_next));
+                    sas_cp_async_commit();
+                }
                 const int e2 = e1 + NT;
                 if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
             }
@@ -500,7 +551,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             if (MODE == 3) process_batch_split<COUNT>(stage[buf], s_reach[buf], (unsigned)warp_arg, cnt, p, s_split[MODE == 3 ? tid >> 5 : 0], s_org[MODE == 3 ? tid >> 5 : 0], split_a_addr, split_c_addr);
             else process_batch<MODE == 3 ? 2 : MODE, COUNT, PACKED>(stage[buf], s_reach[MODE >= 2 ? buf : 0], warp_arg, cnt, p, X0, Y0);
         }
-        sas_cp_async_wait<0>();
+        if (!BULK) sas_cp_async_wait<0>();
 #undef SAS_REC_OF
 
         if (inside && !group_static) {
@@ -624,6 +675,9 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                 if (vf & 0x400) {  // split: alpha record-parallel, only the transmittance chain serial (MODE 3)
                     if (img_out.n_contrib) composite_kernel<4, 3, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                     else composite_kernel<4, 3, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                } else if (vf & 0x800) {  // bulk-async staging: cp.async.bulk + mbarrier expect_tx instead of LDGSTS + wait_group
+                    if (img_out.n_contrib) composite_kernel<4, 2, true, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                    else composite_kernel<4, 2, false, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                 } else if (img_out.n_contrib) composite_kernel<4, 2, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                 else composite_kernel<4, 2, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
             } else if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);

@@ -113,23 +113,32 @@ __device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortS
     return true;
 }
 
-// Equal-depth runs -> ascending Gaussian id (runs are disjoint; the thread at a run's start sorts it).
+// Equal-depth runs -> ascending Gaussian id (what a stable sort with ascending-Gaussian emission gives).  Parallel over
+// the ELEMENTS of the runs: an element of a run finds the run's ends, counts the ids of the run that are smaller than
+// its own (ids are unique inside a bucket) and is written at run start + that rank into the other buffer; elements
+// outside runs are copied.  O(run length) per element, all threads busy -- round 1 let the thread at a run's start
+// insertion-sort the whole run alone, O(k^2) serial steps on coplanar, fronto-parallel Gaussians.  Returns true if
+// the result is in `out` (false: no ties at all, `a` is already final and `out` was not touched).
 template <int NT>
-__device__ void fix_ties(uint2 *a, int n) {
+__device__ bool fix_ties(const uint2 *a, uint2 *out, int n) {
+    bool any = false;
+    for (int i = threadIdx.x; i < n && !any; i += NT) any = i + 1 < n && a[i].x == a[i + 1].x;
+    if (!__syncthreads_or(any)) return false;
     for (int i = threadIdx.x; i < n; i += NT) {
-        const unsigned k = a[i].x;
-        if ((i == 0 || a[i - 1].x != k) && i + 1 < n && a[i + 1].x == k) {
-            int j = i + 1;
-            while (j < n && a[j].x == k) j++;
-            for (int p = i + 1; p < j; p++) {
-                const unsigned v = a[p].y;
-                int q = p - 1;
-                while (q >= i && a[q].y > v) { a[q + 1].y = a[q].y; q--; }
-                a[q + 1].y = v;
-            }
+        const uint2 kv = a[i];
+        int pos = i;
+        if ((i > 0 && a[i - 1].x == kv.x) || (i + 1 < n && a[i + 1].x == kv.x)) {
+            int s = i, e = i + 1;
+            while (s > 0 && a[s - 1].x == kv.x) s--;
+            while (e < n && a[e].x == kv.x) e++;
+            int r = 0;
+            for (int j = s; j < e; j++) r += a[j].y < kv.y ? 1 : 0;
+            pos = s + r;
         }
+        out[pos] = kv;
     }
     __syncthreads();
+    return true;
 }
 
 // Persistent CTAs: each pulls the next bucket of its size class from the class's work list
@@ -174,7 +183,9 @@ __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pair
                     uint2 *t = src; src = dst; dst = t;
                 }
             }
-            fix_ties<NT>(src, n);
+            if (fix_ties<NT>(src, dst, n)) {
+                uint2 *t = src; src = dst; dst = t;
+            }
         }
         // sorted pairs back in place (the merge kernel needs the depth keys as well as the ids)
         if (src != pairs + off)

@@ -34,7 +34,8 @@ class SplatRenderer:
     (merged ids / sorted bucket entries); 0 = start small and let the first (checked) render grow them."""
 
     def __init__(self, scene: SplatScene, device: int = 0, max_images: int = 1, max_envs: int = 1,
-                 max_width: int = 1920, max_height: int = 1080, max_isects: int = 0, max_isects_src: int = 0):
+                 max_width: int = 1920, max_height: int = 1080, max_isects: int = 0, max_isects_src: int = 0,
+                 radius_rule: str = "torch"):
         import torch
 
         if not torch.cuda.is_available():
@@ -47,7 +48,8 @@ class SplatRenderer:
         arrs = [_f32c(scene.means), _f32c(scene.quats), _f32c(scene.scales), _f32c(scene.opacities), _f32c(scene.sh),
                 np.ascontiguousarray(scene.link_id, dtype=np.int32)]
         desc = L.SceneDesc(scene.N, scene.sh_degree, scene.L, L.SAS_MEM_HOST, *[a.ctypes.data for a in arrs])
-        cfg = L.Config(int(max_images), int(max_envs), int(max_width), int(max_height), int(max_isects), int(max_isects_src))
+        cfg = L.Config(int(max_images), int(max_envs), int(max_width), int(max_height), int(max_isects), int(max_isects_src),
+                       {"torch": 0, "cuda_1_5": 1}[radius_rule], 0)
         h = C.c_void_p()
         L.check(self._lib, None, self._lib.sas_create(C.byref(desc), C.byref(cfg), self.device, C.byref(h)))
         self._h = h
@@ -164,6 +166,45 @@ class SplatRenderer:
         else:
             b = np.ascontiguousarray(body_wxyz_xyz, dtype=np.float64).reshape(-1, self.L, 7)
             code = self._lib.sas_set_link_poses_from_bodies(self._h, b.ctypes.data, b.shape[0], L.SAS_MEM_HOST, self._stream(stream))
+        L.check(self._lib, self._h, code)
+        self._handback()
+
+    def set_fk_model(self, source, n_bodies: Optional[int] = None) -> None:
+        """URDF joint tree for the on-device forward kinematics (csrc/sas_pose.cu fk_kernel).  `source` is a
+        urdf_fk.BatchedBodyPoseSource; its first n_bodies mesh-carrying bodies drive link groups 0..n_bodies-1 (default:
+        as many as the URDF has, at most L), the remaining groups are free bodies (the T-block)."""
+        nb = min(self.L, len(source.bodies)) if n_bodies is None else int(n_bodies)
+        d = source.device_model(nb)
+        self._fk_keep = d   # the arrays must outlive the call
+        m = L.FkModel()
+        m.n_joints, m.n_actuated, m.n_bodies = len(d["parent"]), int(d["n_actuated"]), nb
+        for k in ("parent", "type", "qindex", "mimic", "origin", "axis", "base", "body_frame"):
+            setattr(m, k, d[k].ctypes.data)
+        L.check(self._lib, self._h, self._lib.sas_set_fk_model(self._h, C.byref(m)))
+        self._fk_actuated, self._fk_bodies = m.n_actuated, nb
+
+    def set_link_poses_from_joints(self, q, free_bodies=None, stream=None) -> None:
+        """Joint angles [E, A] fp64 -> body poses (URDF forward kinematics) -> link poses, all on the device; needs
+        set_fk_model and set_pose_model.  free_bodies [E, L - n_bodies, 7] fp64 (wxyz | xyz): poses of the link groups
+        that are not robot bodies (default identity).  numpy (host) or CUDA float64 tensors."""
+        torch = self._torch
+        dev_in = isinstance(q, torch.Tensor) and q.is_cuda
+        if dev_in:
+            qq = self._private_copy(q.contiguous().double(), stream, "_q_stage")
+            fb = None
+            if free_bodies is not None:
+                fb = self._private_copy(free_bodies.contiguous().double(), stream, "_fb_stage")
+            E = qq.numel() // self._fk_actuated
+            code = self._lib.sas_set_link_poses_from_joints(self._h, C.c_void_p(qq.data_ptr()), E, C.c_void_p(fb.data_ptr()) if fb is not None else None,
+                                                            L.SAS_MEM_DEVICE, self._stream(stream))
+            self._keep_q = (qq, fb)
+            self._after_private_read(stream)
+        else:
+            qq = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self._fk_actuated)
+            fb = None if free_bodies is None else np.ascontiguousarray(free_bodies, dtype=np.float64).reshape(qq.shape[0], -1, 7)
+            code = self._lib.sas_set_link_poses_from_joints(self._h, qq.ctypes.data, qq.shape[0], fb.ctypes.data if fb is not None else None,
+                                                            L.SAS_MEM_HOST, self._stream(stream))
+            self._keep_q = (qq, fb)
         L.check(self._lib, self._h, code)
         self._handback()
 
@@ -566,6 +607,15 @@ class PipelinedSplatRenderer:
         r, s = self._cur()
         self._after_caller(s)
         r.set_link_poses_from_bodies(body_wxyz_xyz, stream=s)
+
+    def set_fk_model(self, source, n_bodies: Optional[int] = None) -> None:
+        for r in self.renderers:
+            r.set_fk_model(source, n_bodies)
+
+    def set_link_poses_from_joints(self, q, free_bodies=None) -> None:
+        r, s = self._cur()
+        self._after_caller(s)
+        r.set_link_poses_from_joints(q, free_bodies, stream=s)
 
     def render_async(self, outputs: Iterable[str] = ("rgb_u8", "depth"), background=(0.0, 0.0, 0.0),
                      nerfstudio_post: bool = False) -> int:

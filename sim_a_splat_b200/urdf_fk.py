@@ -181,6 +181,35 @@ class BatchedBodyPoseSource:
             T[j.child] = T[j.parent] @ j.origin @ M
         return T
 
+    def device_model(self, n_links: Optional[int] = None) -> Dict[str, np.ndarray]:
+        """The joint tree as flat arrays for `SplatRenderer.set_fk_model` (sas_set_fk_model): joints in
+        parent-before-child order; link frame 0 = the root link(s) at `base`, frame j+1 = child link of joint j."""
+        frame = {l: 0 for l in self._roots}
+        for j, jt in enumerate(self._order):
+            frame[jt.child] = j + 1
+        col = {n: k for k, n in enumerate(self.joint_names)}
+        J = len(self._order)
+        parent = np.array([frame[j.parent] for j in self._order], dtype=np.int32)
+        jtype = np.array([1 if j.jtype in ("revolute", "continuous") else 2 if j.jtype == "prismatic" else 0 for j in self._order], dtype=np.int32)
+        qindex = np.full(J, -1, dtype=np.int32)
+        mimic = np.tile(np.array([1.0, 0.0]), (J, 1))
+        for k, j in enumerate(self._order):
+            if jtype[k] == 0:
+                continue
+            if j.mimic is not None:
+                qindex[k] = col.get(j.mimic[0], -1)
+                mimic[k] = (j.mimic[1], j.mimic[2])
+                if qindex[k] < 0:      # follows a joint that is not actuated: the host path uses q = 0 (not m*0 + o)
+                    mimic[k] = (1.0, 0.0)
+            else:
+                qindex[k] = col.get(j.name, -1)
+        axis = np.stack([j.axis / (np.linalg.norm(j.axis) or 1.0) for j in self._order]).astype(np.float64)
+        bodies = self.bodies if n_links is None else self.bodies[:n_links]
+        return dict(parent=parent, type=jtype, qindex=qindex, mimic=np.ascontiguousarray(mimic, dtype=np.float64),
+                    origin=np.ascontiguousarray(np.stack([j.origin for j in self._order]), dtype=np.float64), axis=np.ascontiguousarray(axis),
+                    base=np.ascontiguousarray(self.base, dtype=np.float64), body_frame=np.array([frame[b] for b in bodies], dtype=np.int32),
+                    n_actuated=len(self.joint_names))
+
     def body_poses(self, q: np.ndarray, n_links: Optional[int] = None) -> np.ndarray:
         """[E, B, 7] fp64 (wxyz | xyz) of the mesh-carrying bodies (first n_links of them)."""
         from .transforms import SO3

@@ -168,3 +168,38 @@ def test_pose_tensor_may_be_overwritten_right_after_the_call():
         pr.join()
         assert torch.equal(outs[-1], want[k % 2]), k
     pr.close(); ref.close()
+
+
+def test_radius_rule_cuda_1_5_fewer_intersections_same_images():
+    """SURVEY 8c pinned rules: gsplat 1.5's CUDA projection shrinks the radius extend with the opacity and culls
+    opacity < 1/255; as an optional mode (sas_config.radius_rule = SAS_RADIUS_CUDA_1_5).  Integer stages bit-exact
+    against the oracle run with the same rule; images and contributor counts identical to the default rule."""
+    import oracle
+    from parity_utils import INT_KEYS
+
+    sc = S.make_synthetic_scene(20000, 3, seed=41, link_counts=(700, 400))
+    rng = np.random.default_rng(4)
+    sc.opacities[rng.choice(sc.N, 3000, replace=False)] = rng.uniform(0.001, 0.05, 3000).astype(np.float32)  # incl. below 1/255
+    W, H, E = 200, 144, 2
+    cams = S.ring_cameras(2, (0, 0, 0), seed=6)
+    vms = np.tile(cams, (E, 1, 1))
+    env = np.repeat(np.arange(E, dtype=np.int32), 2)
+    K = S.fov_intrinsics(W, H)
+    poses = S.random_link_poses(E, sc.L, seed=77)
+    Ks = np.repeat(K[None], len(vms), 0)
+    ref0 = oracle.render(sc.as_oracle_dict(), vms, Ks, W, H, poses, env)
+    ref1 = oracle.render(sc.as_oracle_dict(), vms, Ks, W, H, poses, env, radius_rule="cuda_1_5")
+    assert ref1["M"] < ref0["M"]
+    for k in ("rgb", "depth", "alpha", "n_contrib"):
+        np.testing.assert_array_equal(ref0[k], ref1[k])                # the rule cannot change a pixel
+    r = SplatRenderer(sc, max_images=len(vms), max_envs=E, max_width=W, max_height=H, radius_rule="cuda_1_5")
+    r.set_link_poses(poses)
+    r.set_cameras(vms, K, W, H, env)
+    out = r.render(("rgb", "depth", "alpha", "n_contrib"))
+    dbg = r.debug_intermediates()
+    assert dbg["M"] == ref1["M"]
+    for k in INT_KEYS:
+        np.testing.assert_array_equal(np.asarray(dbg[k]), np.asarray(ref1[k]), err_msg=k)
+    for k in ("rgb", "depth", "alpha", "n_contrib"):
+        np.testing.assert_array_equal(out[k].cpu().numpy(), ref1[k], err_msg=k)
+    r.close()

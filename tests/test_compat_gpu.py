@@ -281,3 +281,47 @@ def test_gaussian_splat_render_contract(toy, assets):
     n_valid = int((d < 1.5).sum())
     assert pts.shape == (n_valid, 3) and cols.shape == (n_valid, 3) and 0 < n_valid < H * W
     assert float(pts[:, 2].max()) < 1.5 and torch.equal(dimg, out["depth"][..., 0])
+
+
+def test_device_urdf_fk_matches_host_body_pose_source(toy, assets):
+    """SURVEY 8f-1 / VERDICT r1 missing #5: joint angles [E,J] -> body poses -> link poses entirely on the device
+    (csrc/sas_pose.cu fk_kernel + link_pose_kernel) == the host chain urdf_fk.BatchedBodyPoseSource.body_poses ->
+    sas_set_link_poses_from_bodies, incl. the prismatic joint, the fixed joint and a free body (the T-block)."""
+    from sim_a_splat_b200.renderer import SplatRenderer
+    from sim_a_splat_b200.splat.splat_handler import RigidTransformLite, SplatHandler
+    from sim_a_splat_b200.urdf_fk import BatchedBodyPoseSource, SimpleURDF
+
+    h = SplatHandler(toy["root"], toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"],
+                     task_assets_name="tblock_paper.obj", sim_robot_weld_frame_transform=RigidTransformLite(translation=(0.03, 0.01, -0.02)))
+    sc = h.server.build_scene()
+    u = SimpleURDF.load(f"{toy['package_path']}/{toy['package_name']}urdf/{toy['urdf_name']}")
+    base = np.eye(4); base[:3, 3] = (0.05, -0.02, 0.01)
+    src = BatchedBodyPoseSource(u, base=base)
+    E, L = 41, sc.L
+    n_robot = min(L, len(src.bodies))
+    if n_robot == L:
+        n_robot = L - 1          # keep one free body in the test: the last link group is then posed by free_bodies
+    r = SplatRenderer(sc, max_images=E, max_envs=E, max_width=64, max_height=64)
+    r.set_pose_model(**h.pose_model())
+    r.set_fk_model(src, n_bodies=n_robot)
+    rng = np.random.default_rng(17)
+    q = rng.uniform(-2.5, 2.5, size=(E, len(src.joint_names))) * np.array([1, 1, 0.1])
+    free = np.concatenate([rng.normal(size=(E, L - n_robot, 4)), rng.uniform(-0.5, 0.5, size=(E, L - n_robot, 3))], axis=-1)
+    # host chain
+    body = np.concatenate([src.body_poses(q, n_links=n_robot), free], axis=1)
+    r.set_link_poses_from_bodies(body)
+    want = r.link_poses(E).copy()
+    # device chain, host inputs then device inputs
+    r.set_link_poses_from_joints(q, free)
+    got = r.link_poses(E).copy()
+    np.testing.assert_allclose(got, want, atol=2e-7, rtol=0)
+    r.set_link_poses_from_joints(torch.from_numpy(q).cuda(), torch.from_numpy(free).cuda())
+    np.testing.assert_array_equal(r.link_poses(E), got)
+    # free bodies default to the identity pose
+    r.set_link_poses_from_joints(q)
+    ident = np.zeros((E, L - n_robot, 7)); ident[..., 0] = 1.0
+    r.set_link_poses_from_bodies(np.concatenate([src.body_poses(q, n_links=n_robot), ident], axis=1))
+    want_i = r.link_poses(E).copy()
+    r.set_link_poses_from_joints(q)
+    np.testing.assert_allclose(r.link_poses(E), want_i, atol=2e-7, rtol=0)
+    r.close()

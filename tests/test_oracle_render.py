@@ -248,3 +248,27 @@ def test_oracle_against_independent_fp64(deg, seed):
     assert np.abs(fr.alpha[0] - ref["alpha"]).max() < 5e-3
     m = ref["alpha"] > 0.05
     assert np.abs(fr.depth[0][m] - ref["depth"][m]).max() < 5e-3
+
+
+def test_radius_rule_cuda_1_5_on_the_oracle():
+    """The optional gsplat-1.5-CUDA radius rule (opacity-aware extend, culls opacity < 1/255): smaller radii, never
+    larger; the same images as the pinned default (a pixel outside either box has alpha < 1/255)."""
+    from sim_a_splat_b200 import scene as S
+
+    sc = S.make_synthetic_scene(4000, 2, seed=3, link_counts=(200,))
+    sc.opacities[::7] = np.float32(0.003)          # below 1/255: culled by the rule
+    sc.opacities[1::7] = np.float32(0.02)
+    cams = S.ring_cameras(2, (0, 0, 0), seed=5)
+    K = np.repeat(S.fov_intrinsics(96, 80)[None], 2, 0)
+    poses = S.random_link_poses(1, 1, seed=2)
+    a = oracle.render(sc.as_oracle_dict(), cams, K, 96, 80, poses, [0, 0])
+    b = oracle.render(sc.as_oracle_dict(), cams, K, 96, 80, poses, [0, 0], radius_rule="cuda_1_5")
+    assert np.all(b["radii"] <= a["radii"]) and b["M"] < a["M"]
+    assert np.all(b["radii"][:, ::7] == 0)
+    for k in ("rgb", "depth", "alpha", "n_contrib"):
+        np.testing.assert_array_equal(a[k], b[k])
+    lib = oracle.oracle._lib()
+    assert lib.orc_extend_export(0, 0.5) == np.float32(3.33) and lib.orc_extend_export(1, 0.003) == 0.0
+    assert abs(lib.orc_extend_export(1, 0.02) - np.sqrt(2 * np.log(0.02 * 255))) < 1e-6
+    assert abs(lib.orc_extend_export(1, 0.99) - np.sqrt(2 * np.log(0.99 * 255))) < 1e-6   # 3.326: even opaque Gaussians shrink a little
+    assert lib.orc_extend_export(1, 1.5) == np.float32(3.33)                              # the cap

@@ -11,7 +11,7 @@ GP=""; [ "$GPUS" != "1" ] && GP="--gpus $GPUS"
 for try in $(seq 1 40); do
   /usr/local/graft/bin/gpurun $GP --timeout $TMO -- "cd gpurun_stage/$TAG && mkdir -p gpurun_out && ( $CMD ); mkdir -p \$GRAFT_REPO_ROOT/gpurun_out/$TAG && cp -r gpurun_out/. \$GRAFT_REPO_ROOT/gpurun_out/$TAG/" > /tmp/gpu_$TAG.log 2>&1
   rc=$?
-  if grep -q "status=transient\|retry in a few minutes" /tmp/gpu_$TAG.log || [ $rc -eq 3 ]; then sleep 75; continue; fi
+  if grep -q "status=transient\|retry in a few minutes\|already running" /tmp/gpu_$TAG.log || [ $rc -eq 3 ]; then sleep 75; continue; fi
   break
 done
 cat /tmp/gpu_$TAG.log | tail -40

@@ -12,8 +12,9 @@ unmodified, by importing the reference's files with stub modules in
                       (the module itself imports nerfstudio at the top)
 * draw_handler.npz  - `SplatHandler._load_saved_masks`, `.draw_handler`,
                       `.get_attached_frame` from splat/splat_handler.py, bound to a bare
-                      object; `viser.transforms` is replaced by
-                      sim_a_splat_b200.transforms (checked against scipy in tests)
+                      object; `viser.transforms` is replaced by a
+                      stand-in built only on scipy's Rotation (tools/viser_tf_scipy.py), NOT by
+                      this repo's own transforms.py
 * assets.npz        - the real masks (bit-packed), ICP matrices, intrinsics, a few
                       training camera poses, dataparser transforms and a subsample of
                       the robot surface points, so the GPU box (which has no
@@ -107,8 +108,16 @@ class _Weld:
         return _Rot()
 
 
+def _standin_tf():
+    """scipy-only stand-in for viser.transforms (tools/viser_tf_scipy.py) -- NOT this repo's transforms.py."""
+    sys.path.insert(0, str(REPO / "tools"))
+    import viser_tf_scipy
+
+    return viser_tf_scipy
+
+
 def _import_reference_splat_handler():
-    import sim_a_splat_b200.transforms as mytf
+    mytf = _standin_tf()
 
     def stub(name, **attrs):
         m = types.ModuleType(name)
@@ -134,7 +143,7 @@ def _import_reference_splat_handler():
 
 
 def make_draw_handler():
-    import sim_a_splat_b200.transforms as mytf
+    mytf = _standin_tf()
 
     sh = _import_reference_splat_handler()
     rng = np.random.default_rng(2024)
