@@ -124,7 +124,7 @@ def algorithmic_bytes(st: dict, N: int, K_sh: int, out_bytes_per_px: int) -> dic
     }
 
 
-def time_workload(torch, name, wl, steps, device, max_images=None, max_isects=0, max_isects_src=0):
+def time_workload(torch, name, wl, steps, device, max_images=None, max_isects=0, max_isects_src=0, radius_rule="torch"):
     """ms/step, frames/s and per-stage times of one workload (device-resident poses, one step at a time)."""
     from sim_a_splat_b200.renderer import SplatRenderer
 
@@ -132,7 +132,7 @@ def time_workload(torch, name, wl, steps, device, max_images=None, max_isects=0,
     I = vms.shape[0]
     E = 1 if poses is None else poses.shape[0]
     r = SplatRenderer(sc, device=device, max_images=max_images or I, max_envs=E, max_width=w, max_height=h, max_isects=max_isects,
-                      max_isects_src=max_isects_src)
+                      max_isects_src=max_isects_src, radius_rule=radius_rule)
     pd = torch.from_numpy(poses).to(f"cuda:{device}") if sc.L else None
     if sc.L:
         r.set_link_poses(pd)
@@ -179,6 +179,10 @@ def other_configs(torch, device, steps):
                              WL.config3_divar(2048, 0, 256), steps, device, max_isects=120_000_000, max_isects_src=40_000_000))
     res.append(time_workload(torch, "configs[4] synthetic 6 M Gaussians SH-3, 1920x1080, 8 of the 64 cameras per call",
                              WL.config4_stress(8), max(steps // 4, 3), device))
+    # the bench workload under gsplat 1.5's CUDA radius rule (opacity-aware extend; identical images, fewer intersections):
+    # reported for information, the headline uses the pinned default rule
+    res.append(time_workload(torch, "configs[1] with radius_rule=cuda_1_5 (one step at a time; compare with 'serial')", WL.config1_pusht(E_PER_GPU),
+                             steps * 2, device, max_isects=CAP_ALL, max_isects_src=CAP_SRC, radius_rule="cuda_1_5"))
     return res
 
 

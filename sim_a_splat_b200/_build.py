@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libsas_b200.so"
-SOURCES = ["sas_api.cu", "sas_project.cu", "sas_bin.cu", "sas_work.cu", "sas_sort.cu", "sas_composite.cu", "sas_pose.cu"]
+SOURCES = ["sas_api.cu", "sas_project.cu", "sas_bin.cu", "sas_work.cu", "sas_sort.cu", "sas_binsort.cu", "sas_composite.cu", "sas_pose.cu"]
 # -fmad=false: no implicit FMA contraction anywhere (numerics contract, csrc/sas_common.cuh);
 # fused multiply-adds exist only where fmaf() is written.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

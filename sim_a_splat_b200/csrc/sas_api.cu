@@ -7,6 +7,7 @@
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: stage ranges for nsys / ncu --nvtx filtering
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,11 @@ struct sas_renderer {
     float4 *mean_op = nullptr, *quat = nullptr, *scale_link = nullptr;
     float *sh_planes = nullptr;
     float *extend = nullptr;             // per-Gaussian radius extend (radius_rule = cuda_1_5), else null
+    // INTERNAL order of the background Gaussians: Morton order of their means (spatially close Gaussians sit next to
+    // each other, so a CTA's 256 Gaussians project into neighbouring tiles and the emission writes each bucket in
+    // contiguous runs).  canon_of[internal] = canonical index; null = the internal order is the canonical one.
+    int *canon_of = nullptr;
+    std::vector<int> h_canon;
     // per-call state
     float *link_poses = nullptr;
     int n_envs = 0;
@@ -282,17 +288,65 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
         }
     r->n_bg = n_bg; r->n_dyn = N - n_bg;
 
+    // Optional internal order (SAS_MORTON=1): background by the Morton code of the mean (10 bits per axis over the
+    // background's bounding box, canonical index as the tie-break), link Gaussians as they are.  Measured (round 2b,
+    // profiles/r02b_morton_order.txt): emission of the 6 M-Gaussian 1080p chunk 11.8 -> 9.8 ms, but the Gaussians of a CTA
+    // then hit the SAME few tiles and serialise on the shared-memory histogram atomics of projection and emission --
+    // configs[2] emission 0.065 -> 0.192 ms, projection 0.080 -> 0.110 ms.  Off by default.
+    std::vector<int> order(N);
+    for (int g = 0; g < N; g++) order[g] = g;
+    {
+        const char *em = getenv("SAS_MORTON");
+        const char *es = getenv("SAS_SORT");
+        const bool want = (em && atoi(em) != 0) && !(es && es[0] == 'b') && n_bg > 1;
+        if (want) {
+            float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+            for (int g = 0; g < n_bg; g++)
+                for (int a = 0; a < 3; a++) {
+                    const float v = h_means[3 * g + a];
+                    if (v == v) { lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
+                }
+            std::vector<unsigned long long> code(n_bg);
+            auto spread = [](unsigned v) {  // 10 bits -> every third bit
+                unsigned long long x = v & 0x3ffu;
+                x = (x | (x << 16)) & 0x030000ffull;
+                x = (x | (x << 8)) & 0x0300f00full;
+                x = (x | (x << 4)) & 0x030c30c3ull;
+                x = (x | (x << 2)) & 0x09249249ull;
+                return x;
+            };
+            for (int g = 0; g < n_bg; g++) {
+                unsigned q[3];
+                for (int a = 0; a < 3; a++) {
+                    const float ext = hi[a] - lo[a];
+                    float t = ext > 0.0f ? (h_means[3 * g + a] - lo[a]) / ext : 0.0f;
+                    if (!(t >= 0.0f)) t = 0.0f;
+                    if (t > 1.0f) t = 1.0f;
+                    q[a] = (unsigned)(t * 1023.0f);
+                }
+                code[g] = ((spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2)) << 32) | (unsigned)g;
+            }
+            std::sort(code.begin(), code.end());
+            r->h_canon.resize(n_bg);
+            for (int i = 0; i < n_bg; i++) { order[i] = (int)(code[i] & 0xffffffffull); r->h_canon[i] = order[i]; }
+        }
+    }
     std::vector<float4> p_mean(N), p_quat(N), p_scale(N);
     std::vector<float> p_sh((size_t)K * 3 * r->n_pad, 0.0f);
-    for (int g = 0; g < N; g++) {
-        p_mean[g] = make_float4(h_means[3 * g], h_means[3 * g + 1], h_means[3 * g + 2], h_op[g]);
-        p_quat[g] = make_float4(h_quats[4 * g], h_quats[4 * g + 1], h_quats[4 * g + 2], h_quats[4 * g + 3]);
+    for (int i = 0; i < N; i++) {
+        const int g = order[i];  // canonical index of the Gaussian at internal position i
+        p_mean[i] = make_float4(h_means[3 * g], h_means[3 * g + 1], h_means[3 * g + 2], h_op[g]);
+        p_quat[i] = make_float4(h_quats[4 * g], h_quats[4 * g + 1], h_quats[4 * g + 2], h_quats[4 * g + 3]);
         float lid;
         int32_t li = h_link[g] < 0 ? -1 : h_link[g];
         memcpy(&lid, &li, 4);
-        p_scale[g] = make_float4(h_scales[3 * g], h_scales[3 * g + 1], h_scales[3 * g + 2], lid);
+        p_scale[i] = make_float4(h_scales[3 * g], h_scales[3 * g + 1], h_scales[3 * g + 2], lid);
         for (int k = 0; k < K; k++)
-            for (int ch = 0; ch < 3; ch++) p_sh[(size_t)(3 * k + ch) * r->n_pad + g] = h_sh[((size_t)g * K + k) * 3 + ch];
+            for (int ch = 0; ch < 3; ch++) p_sh[(size_t)(3 * k + ch) * r->n_pad + i] = h_sh[((size_t)g * K + k) * 3 + ch];
+    }
+    if (!r->h_canon.empty()) {
+        SAS_CUDA_C(cudaMalloc(&r->canon_of, sizeof(int) * n_bg));
+        SAS_CUDA_C(cudaMemcpy(r->canon_of, r->h_canon.data(), sizeof(int) * n_bg, cudaMemcpyHostToDevice));
     }
     SAS_CUDA_C(cudaMalloc(&r->mean_op, sizeof(float4) * N));
     SAS_CUDA_C(cudaMalloc(&r->quat, sizeof(float4) * N));
@@ -306,13 +360,14 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
         // the same double-precision expression, rounded once to float, as oracle/splat_oracle.c:orc_extend
         std::vector<float> ext(N);
         const float amin = 1.0f / 255.0f;
-        for (int g = 0; g < N; g++) {
+        for (int i = 0; i < N; i++) {
+            const float op = h_op[order[i]];
             float e = 0.0f;
-            if (!(h_op[g] < amin)) {
-                e = (float)sqrt(2.0 * log((double)h_op[g] / (double)amin));
+            if (!(op < amin)) {
+                e = (float)sqrt(2.0 * log((double)op / (double)amin));
                 if (!(e < 3.33f)) e = 3.33f;
             }
-            ext[g] = e;
+            ext[i] = e;
         }
         SAS_CUDA_C(cudaMalloc(&r->extend, sizeof(float) * N));
         SAS_CUDA_C(cudaMemcpy(r->extend, ext.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
@@ -357,7 +412,7 @@ void sas_destroy(sas_renderer *r) {
     cudaSetDevice(r->device);
     cudaDeviceSynchronize();
     cudaFree(r->mean_op); cudaFree(r->quat); cudaFree(r->scale_link); cudaFree(r->sh_planes);
-    cudaFree(r->fk_dev); cudaFree(r->extend);
+    cudaFree(r->fk_dev); cudaFree(r->extend); cudaFree(r->canon_of);
     cudaFree(r->link_poses); cudaFree(r->row_cams); cudaFree(r->view_of_image); cudaFree(r->counters); cudaFree(r->snap);
     if (r->h_snap) cudaFreeHost(r->h_snap);
     if (r->stage_host) cudaFreeHost(r->stage_host);
@@ -725,8 +780,8 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     }
     if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, cap_src, st, r->aux, r->fork_ev,
-                                     &launches));
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, cap_src, r->canon_of, r->n_bg, st, r->aux,
+                                     r->fork_ev, &launches));
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, cap_src, cap_all,
                                  (sas_variant_flags() & 8) ? 0 : 1, (const int *)r->comp_list.p, work, st));
     launches += 1;
@@ -1014,7 +1069,29 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
         default: return fail(r, SAS_EINVAL, "sas_debug_fetch: unknown item");
     }
     if (bytes > avail) return fail(r, SAS_EINVAL, "sas_debug_fetch: more bytes requested than available");
-    if (bytes) SAS_CUDA(r, cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost));
+    if (!bytes) return SAS_OK;
+    const bool rows = what == SAS_DBG_RECORDS || what == SAS_DBG_BINS || what == SAS_DBG_RADII;
+    if (r->h_canon.empty() || !(rows || what == SAS_DBG_SORTED_GIDS)) {
+        SAS_CUDA(r, cudaMemcpy(dst_host, src, bytes, cudaMemcpyDeviceToHost));
+        return SAS_OK;
+    }
+    // the background lives in the internal (Morton) order on the device: hand it out in the canonical order
+    std::vector<unsigned char> tmp(avail);
+    SAS_CUDA(r, cudaMemcpy(tmp.data(), src, avail, cudaMemcpyDeviceToHost));
+    if (rows) {
+        const size_t es = what == SAS_DBG_RECORDS ? sizeof(SasRecord) : 8;
+        std::vector<unsigned char> view((size_t)r->n_bg * es);
+        for (int v = 0; v < r->C; v++) {
+            unsigned char *base = tmp.data() + (size_t)v * r->n_bg * es;
+            for (int i = 0; i < r->n_bg; i++) memcpy(view.data() + (size_t)r->h_canon[i] * es, base + (size_t)i * es, es);
+            memcpy(base, view.data(), view.size());
+        }
+    } else {
+        int *ids = reinterpret_cast<int *>(tmp.data());
+        for (size_t k = 0; k < avail / 4; k++)
+            if (ids[k] >= 0 && ids[k] < r->n_bg) ids[k] = r->h_canon[ids[k]];
+    }
+    memcpy(dst_host, tmp.data(), bytes);
     return SAS_OK;
 }
 

@@ -265,9 +265,14 @@ cudaError_t sas_launch_scan(const unsigned int *counts, int n, const int *view_o
 cudaError_t sas_launch_emit(const uint2 *bins, SasRowSpan span, int tile_w, int tile_h, const int *row_tile_offset,
                             unsigned int *row_tile_cursor, uint2 *pairs, long long capacity, cudaStream_t st);
 cudaError_t sas_sort_init(int n_sms);
+cudaError_t sas_binsort_init();
+// the four shared-memory size classes as bin sorts (sas_binsort.cu); class c on stream s_of[c]
+cudaError_t sas_launch_bin_sort(uint2 *pairs, const int *row_tile_offset, const int *sort_list, SasWork *work, long long capacity, int n_sms,
+                                cudaStream_t *s_of);
 // aux / ev: SAS_SORT_CLASSES - 1 side streams and 2 * SAS_SORT_CLASSES events for the fork / join (may be null: serial)
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
-                                 long long capacity, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
+                                 long long capacity, const int *canon_of /*internal -> canonical id of background Gaussians, or null*/,
+                                 int n_bg, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
 // fill_static: also write the ids of tiles whose link bucket is empty (the compositor never reads those)
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,

@@ -19,6 +19,8 @@
 // HBM traffic: 8 B read + 8 B written per bucket entry.
 #include "sas_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 template <int NT>
@@ -119,8 +121,12 @@ __device__ bool radix_pass(const uint2 *src, uint2 *dst, int n, int shift, SortS
 // outside runs are copied.  O(run length) per element, all threads busy -- round 1 let the thread at a run's start
 // insertion-sort the whole run alone, O(k^2) serial steps on coplanar, fronto-parallel Gaussians.  Returns true if
 // the result is in `out` (false: no ties at all, `a` is already final and `out` was not touched).
+// canon_of (may be null): the library stores the background Gaussians in a spatially sorted INTERNAL order
+// (sas_api.cu: Morton order of the means, so that a CTA's Gaussians fall into neighbouring tiles); the ids in the pairs
+// are internal, the tie order the reference defines is by CANONICAL id: canon_of[internal] for ids below n_bg, the id
+// itself for link Gaussians.
 template <int NT>
-__device__ bool fix_ties(const uint2 *a, uint2 *out, int n) {
+__device__ bool fix_ties(const uint2 *a, uint2 *out, int n, const int *__restrict__ canon_of, int n_bg) {
     bool any = false;
     for (int i = threadIdx.x; i < n && !any; i += NT) any = i + 1 < n && a[i].x == a[i + 1].x;
     if (!__syncthreads_or(any)) return false;
@@ -132,7 +138,15 @@ __device__ bool fix_ties(const uint2 *a, uint2 *out, int n) {
             while (s > 0 && a[s - 1].x == kv.x) s--;
             while (e < n && a[e].x == kv.x) e++;
             int r = 0;
-            for (int j = s; j < e; j++) r += a[j].y < kv.y ? 1 : 0;
+            if (canon_of) {
+                const unsigned mine = (int)kv.y < n_bg ? (unsigned)__ldg(canon_of + kv.y) : kv.y;
+                for (int j = s; j < e; j++) {
+                    const unsigned y = a[j].y;
+                    r += ((int)y < n_bg ? (unsigned)__ldg(canon_of + y) : y) < mine ? 1 : 0;
+                }
+            } else {
+                for (int j = s; j < e; j++) r += a[j].y < kv.y ? 1 : 0;
+            }
             pos = s + r;
         }
         out[pos] = kv;
@@ -146,7 +160,7 @@ __device__ bool fix_ties(const uint2 *a, uint2 *out, int n) {
 template <int NT, bool IN_GLOBAL>
 __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pairs_alt, const int *__restrict__ tile_offset,
                                                        const int *__restrict__ sort_list, SasWork *work, int cls, int cap,
-                                                       long long max_isects) {
+                                                       long long max_isects, const int *__restrict__ canon_of, int n_bg) {
     constexpr int SORT_THREADS = NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortShared<NT> &sh = *reinterpret_cast<SortShared<NT> *>(smem_raw);
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pair
                     uint2 *t = src; src = dst; dst = t;
                 }
             }
-            if (fix_ties<NT>(src, dst, n)) {
+            if (fix_ties<NT>(src, dst, n, canon_of, n_bg)) {
                 uint2 *t = src; src = dst; dst = t;
             }
         }
@@ -197,12 +211,16 @@ template <int NT>
 size_t sort_smem(int cap) { return sizeof(SortShared<NT>) + 2 * (size_t)cap * sizeof(uint2); }
 
 int g_sort_sms = 148;
+int g_sort_radix = 1;  // SAS_SORT=bin: the bin sort of sas_binsort.cu for the shared-memory classes (measured slower, see there); default: LSD radix
 
 }  // namespace
 
 cudaError_t sas_sort_init(int n_sms) {
     g_sort_sms = n_sms > 0 ? n_sms : 148;
-    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (const char *ev = getenv("SAS_SORT")) g_sort_radix = (ev[0] != 'b');
+    cudaError_t e = sas_binsort_init();
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sort_smem<512>(SAS_SORT_CAP3));
     return e;
 }
@@ -211,7 +229,8 @@ cudaError_t sas_sort_init(int n_sms) {
 // (fork on an event of the caller's stream, join back into it): the step pays for the slowest class
 // instead of the sum of five partially filled launches.
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
-                                 long long capacity, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches) {
+                                 long long capacity, const int *canon_of, int n_bg, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev,
+                                 int *n_launches) {
     // grid = SMs x resident CTAs of the class (threads / shared memory bound)
     const int sms = g_sort_sms;
     const bool fork = aux != nullptr && ev != nullptr && (sas_variant_flags() & 4);
@@ -226,17 +245,21 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
             if ((e = cudaStreamWaitEvent(aux[k], ev[0], 0)) != cudaSuccess) return e;
         }
     }
+    if (!g_sort_radix) {
+        if ((e = sas_launch_bin_sort(pairs, row_tile_offset, sort_list, work, capacity, sms, s_of)) != cudaSuccess) return e;
+    } else {
     tile_sort_kernel<512, false><<<sms * 2, 512, sort_smem<512>(SAS_SORT_CAP2), s_of[2]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 2,
-                                                                                         SAS_SORT_CAP2, capacity);
+                                                                                         SAS_SORT_CAP2, capacity, canon_of, n_bg);
     tile_sort_kernel<512, false><<<sms, 512, sort_smem<512>(SAS_SORT_CAP3), s_of[3]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 3,
-                                                                                     SAS_SORT_CAP3, capacity);
+                                                                                     SAS_SORT_CAP3, capacity, canon_of, n_bg);
     tile_sort_kernel<256, false><<<sms * 5, 256, sort_smem<256>(SAS_SORT_CAP1), s_of[1]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 1,
-                                                                                         SAS_SORT_CAP1, capacity);
+                                                                                         SAS_SORT_CAP1, capacity, canon_of, n_bg);
     tile_sort_kernel<128, false><<<sms * 16, 128, sort_smem<128>(SAS_SORT_CAP0), s_of[0]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 0,
-                                                                                          SAS_SORT_CAP0, capacity);
+                                                                                          SAS_SORT_CAP0, capacity, canon_of, n_bg);
+    }
     // buckets beyond shared memory: 32 warps per CTA (measured on the 6 M-Gaussian 1080p chunk: sort 26.5 -> 19.5 ms)
     tile_sort_kernel<1024, true><<<sms, 1024, sizeof(SortShared<1024>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0,
-                                                                                  capacity);
+                                                                                  capacity, canon_of, n_bg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (fork)
         for (int k = 0; k < 4; k++) {
