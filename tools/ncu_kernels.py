@@ -17,7 +17,7 @@ import re
 import subprocess
 import sys
 
-STAGE_OF = [("project_kernel", "project"), ("scan_", "scan"), ("work_", "scan"), ("emit_kernel", "emit"), ("tile_sort_kernel", "sort"),
+STAGE_OF = [("project_", "project"), ("scan_", "scan"), ("work_", "scan"), ("emit_kernel", "emit"), ("tile_sort_kernel", "sort"),
             ("merge_", "sort"), ("composite_kernel", "composite"), ("copy_static_tiles", "composite"), ("ns_", "post"),
             ("snapshot_kernel", "post"), ("link_pose_kernel", "pose"), ("fk_kernel", "pose")]
 
@@ -114,7 +114,7 @@ def main(path, out):
             c["evaluated_pairs"] = int(pairs)
             break
     res["_kernels"] = kernels
-    res["_source"] = f"tools/ncu_kernels.py {path}: ncu --set full --clock-control none --import-source on, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs; per-step sums of per-launch averages by (kernel, grid)"
+    res["_source"] = f"tools/ncu_kernels.py {path}: ncu --set full --clock-control none -s 60 -c 26, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs; per-step sums of per-launch averages by (kernel, grid)"
     json.dump(res, open(out, "w"), indent=1)
     for k, v in res.items():
         if not k.startswith("_"):
