@@ -396,3 +396,52 @@ def test_renderer_without_cuda_fails_loudly(toy):
     env.reset(seed=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         env.step(np.zeros(3))
+
+
+def test_urdf_fk_on_the_reference_robot_descriptions(golden_dir, tmp_path):
+    """the visual-mesh FK (what the reference gets from urchin's visual_trimesh_fk, splat_handler.py:158-163,
+    :197) on the reference's REAL robot descriptions -- xarm6 with push gripper (8 visual meshes for 7 masks) and
+    divar113vhw -- against transforms computed at fixture time by an implementation built on scipy's Rotation that shares
+    nothing with urdf_fk.py (tools/make_golden.py:make_urdf_fk), at the capture configuration and at a random one; the
+    batched body-pose source and its flat device model agree with it too."""
+    from sim_a_splat_b200.urdf_fk import BatchedBodyPoseSource
+
+    g = np.load(golden_dir / "urdf_fk.npz")
+    for name, n_vis in (("xarm6", 8), ("divar113vhw", 6)):
+        path = tmp_path / f"{name}.urdf"
+        path.write_text(str(g[f"{name}/urdf"]))
+        u = SimpleURDF.load(str(path))
+        assert u.actuated_joint_names == [str(v) for v in g[f"{name}/actuated"]]
+        for which in ("capture", "random"):
+            q = g[f"{name}/q_{which}"]
+            vis = u.visual_mesh_fk(dict(zip(u.actuated_joint_names, [float(v) for v in q])))
+            assert len(vis) == n_vis
+            np.testing.assert_allclose(np.stack(vis), g[f"{name}/fk_{which}"], atol=1e-12)
+        src = BatchedBodyPoseSource(u)
+        T = src.link_fk(np.stack([g[f"{name}/q_capture"], g[f"{name}/q_random"]]))
+        vm = u.mesh_visuals()
+        for k, which in enumerate(("capture", "random")):
+            for i, v in enumerate(vm):
+                np.testing.assert_allclose(T[v.link][k] @ v.origin, g[f"{name}/fk_{which}"][i], atol=1e-12)
+        d = src.device_model()
+        assert d["parent"].shape[0] == len(u.joints) and np.all(d["parent"] <= np.arange(len(u.joints)))   # parent-before-child
+        assert int(d["n_actuated"]) == len(u.actuated_joint_names) and d["body_frame"].shape[0] == n_vis
+
+
+def test_missing_joint_config_is_reported_and_can_be_supplied(toy, tmp_path):
+    """divar113vhw ships without masks/<obj>/joint_config.npy, so the reference cannot build that scene; here the
+    constructor argument takes the file's place and a missing file says what to do."""
+    import shutil
+
+    root = tmp_path / "assets"
+    shutil.copytree(toy["root"], root)
+    jc = root / "masks" / toy["obj"] / "joint_config.npy"
+    want = np.load(jc)
+    ref = _handler(toy)
+    jc.unlink()
+    kw = dict(task_assets_name="tblock_paper.obj")
+    with pytest.raises(FileNotFoundError, match="joint_config"):
+        SplatHandler(str(root), toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"], **kw)
+    h = SplatHandler(str(root), toy["obj"], toy["cfg"], toy["package_path"], toy["package_name"], toy["urdf_name"], joint_config=want, **kw)
+    for a, b in zip(h.fk_tf, ref.fk_tf):
+        np.testing.assert_allclose(a.as_matrix(), b.as_matrix(), atol=1e-12)

@@ -249,9 +249,105 @@ def make_assets():
     print("assets.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim > 0})
 
 
+def make_urdf_fk():
+    """Visual-mesh forward kinematics of the reference's REAL robot descriptions (xarm6 with push gripper, divar113vhw)
+    by an implementation that shares nothing with sim_a_splat_b200/urdf_fk.py: ElementTree + scipy Rotation
+    (URDF rpy = Rotation.from_euler('xyz', rpy) in scipy's extrinsic convention; joint motion = from_rotvec(axis q)).
+    The fixture holds a STRIPPED copy of each URDF (links, visual origins, joint tree: the numbers the FK needs, none of
+    the inertial / collision / material blocks) so that the test can run the product parser without /root/reference,
+    plus the transforms at the capture-time configuration (zeros for the xarm, match_splat.py:67's [0.2, 3.0, 3.14, 0, 0]
+    for divar113vhw, whose joint_config.npy is absent from the assets) and at a random configuration."""
+    import xml.etree.ElementTree as ET
+
+    from scipy.spatial.transform import Rotation as R
+
+    def H(el):
+        T = np.eye(4)
+        if el is not None:
+            T[:3, :3] = R.from_euler("xyz", [float(v) for v in el.get("rpy", "0 0 0").split()]).as_matrix()
+            T[:3, 3] = [float(v) for v in el.get("xyz", "0 0 0").split()]
+        return T
+
+    out = {}
+    rng = np.random.default_rng(77)
+    for name, path, q0 in (("xarm6", REF / "robot_description/xarm_description/xarm6/urdf/xarm6_with_push_gripper.urdf", None),
+                           ("divar113vhw", REF / "robot_description/divar113vhw/urdf/divar113vhw.urdf", [0.2, 3.0, 3.14, 0, 0])):
+        root = ET.parse(path).getroot()
+        links = [l.get("name") for l in root.findall("link")]
+        joints = root.findall("joint")
+        act = [j.get("name") for j in joints if j.get("type") in ("revolute", "continuous", "prismatic") and j.find("mimic") is None]
+        # stripped URDF
+        lines = [f'<robot name="{name}">']
+        for l in root.findall("link"):
+            lines.append(f'  <link name="{l.get("name")}">')
+            for v in l.findall("visual"):
+                o, g = v.find("origin"), v.find("geometry")
+                mesh = g.find("mesh") if g is not None else None
+                lines.append("    <visual>")
+                if o is not None:
+                    lines.append(f'      <origin xyz="{o.get("xyz", "0 0 0")}" rpy="{o.get("rpy", "0 0 0")}"/>')
+                lines.append(f'      <geometry>{"<mesh filename=" + chr(34) + mesh.get("filename") + chr(34) + "/>" if mesh is not None else "<box size=" + chr(34) + "1 1 1" + chr(34) + "/>"}</geometry>')
+                lines.append("    </visual>")
+            lines.append("  </link>")
+        for j in joints:
+            o, ax, mim = j.find("origin"), j.find("axis"), j.find("mimic")
+            lines.append(f'  <joint name="{j.get("name")}" type="{j.get("type")}">')
+            lines.append(f'    <parent link="{j.find("parent").get("link")}"/><child link="{j.find("child").get("link")}"/>')
+            if o is not None:
+                lines.append(f'    <origin xyz="{o.get("xyz", "0 0 0")}" rpy="{o.get("rpy", "0 0 0")}"/>')
+            if ax is not None:
+                lines.append(f'    <axis xyz="{ax.get("xyz")}"/>')
+            if mim is not None:
+                lines.append(f'    <mimic joint="{mim.get("joint")}" multiplier="{mim.get("multiplier", "1")}" offset="{mim.get("offset", "0")}"/>')
+            lines.append("  </joint>")
+        lines.append("</robot>")
+        out[f"{name}/urdf"] = np.array("\n".join(lines))
+        out[f"{name}/actuated"] = np.array(act)
+
+        def fk(q):
+            cfg = dict(zip(act, q))
+            children = {j.find("child").get("link") for j in joints}
+            T = {l: np.eye(4) for l in links if l not in children}
+            pend = list(joints)
+            while pend:
+                for j in list(pend):
+                    par = j.find("parent").get("link")
+                    if par not in T:
+                        continue
+                    qj = cfg.get(j.get("name"), 0.0)
+                    mim = j.find("mimic")
+                    if mim is not None:
+                        qj = cfg.get(mim.get("joint"), 0.0) * float(mim.get("multiplier", 1)) + float(mim.get("offset", 0))
+                    ax = j.find("axis")
+                    a = np.array([float(v) for v in ax.get("xyz").split()]) if ax is not None else np.array([1.0, 0, 0])
+                    a = a / (np.linalg.norm(a) or 1.0)
+                    M = np.eye(4)
+                    if j.get("type") in ("revolute", "continuous"):
+                        M[:3, :3] = R.from_rotvec(a * qj).as_matrix()
+                    elif j.get("type") == "prismatic":
+                        M[:3, 3] = a * qj
+                    T[j.find("child").get("link")] = T[par] @ H(j.find("origin")) @ M
+                    pend.remove(j)
+            vis = []
+            for l in root.findall("link"):
+                for v in l.findall("visual"):
+                    g = v.find("geometry")
+                    if g is not None and g.find("mesh") is not None:
+                        vis.append(T[l.get("name")] @ H(v.find("origin")))
+            return np.stack(vis)
+
+        q_cap = np.zeros(len(act)) if q0 is None else np.asarray(q0, dtype=np.float64)[: len(act)]
+        q_rnd = rng.uniform(-1.5, 1.5, len(act))
+        out[f"{name}/q_capture"], out[f"{name}/q_random"] = q_cap, q_rnd
+        out[f"{name}/fk_capture"], out[f"{name}/fk_random"] = fk(q_cap), fk(q_rnd)
+    np.savez_compressed(OUT / "urdf_fk.npz", **out)
+    print("urdf_fk.npz", {k: v.shape for k, v in out.items() if getattr(v, "ndim", 0) > 0})
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     make_compute_cov()
     make_sh2rgb()
     make_draw_handler()
     make_assets()
+    make_urdf_fk()
