@@ -53,7 +53,7 @@ struct sas_renderer {
     bool cameras_set = false;
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
-    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask;
+    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask, big_items;
     SasPoseModel pose_model{};            // device pointers inside; pose_model.L == 0: not set
     double *fk_dev = nullptr;             // [L,15]: fk_R, fk_t, body_offset
     DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
@@ -82,13 +82,17 @@ struct sas_renderer {
     unsigned long long render_seq = 0;   // renders issued (== ring->seq once they have run)
     unsigned long long ovf_floor = 0;    // renders before this one are not reported any more (reserve / poll)
     int max_env_index = 0;               // largest env an image of the current camera set refers to
+    // Has this renderer seen tile lists long enough for the multi-CTA big-bucket sort (sas_sort.cu)?  Set from the
+    // counters the host reads anyway (stats, overflow polls, snapshots that travel with host outputs); until then the
+    // step's graph does not carry that path's launches.  A hint: correctness does not depend on it.
+    bool big_hint = false;
     bool rendered = false;
     int last_launches = 0;
     bool stage_timing = false;
     cudaEvent_t stage_ev[SAS_N_STAGES + 1] = {};
     // CUDA graph of the device work of one sas_render (captured on first use, replayed while the key matches)
     struct GraphKey {
-        int I, C, W, H, ns, flags;
+        int I, C, W, H, ns, flags, big;
         float bg[3];
         void *rgb, *depth, *alpha, *u8, *nc, *f16;
         long long max_isects, max_isects_src;
@@ -177,6 +181,10 @@ PackedLayout packed_layout(size_t P, int want) {
             l.total = (l.total + P * kBytes[k] + 255) & ~(size_t)255;
         }
     return l;
+}
+
+void note_counters(sas_renderer *r, const SasCounters &c) {
+    if ((long long)c.max_tile_list > SAS_SORT_CAP3) r->big_hint = true;
 }
 
 int overflow_error(sas_renderer *r, const SasCounters &c, const char *who) {
@@ -436,7 +444,7 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_alpha[0], &r->o_pack[0], &r->o_pack[1],
-                      &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid,
+                      &r->big_items, &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid,
                       &r->fk_blob, &r->fk_q, &r->fk_extra};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
@@ -780,7 +788,8 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     }
     if (two_spans) SAS_CUDA(r, join_span());
     SAS_STAGE(3);
-    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, cap_src, r->canon_of, r->n_bg, st, r->aux,
+    SAS_CUDA(r, sas_launch_tile_sort(pairs, pairs_alt, roff, (const int *)r->sort_list.p, work, cap_src, r->canon_of, r->n_bg,
+                                     (int2 *)r->big_items.p, (int)(r->big_items.bytes / sizeof(int2)), r->big_hint ? 1 : 0, st, r->aux,
                                      r->fork_ev, &launches));
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, cap_src, cap_all,
                                  (sas_variant_flags() & 8) ? 0 : 1, (const int *)r->comp_list.p, work, st));
@@ -854,6 +863,10 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         if (!d_alpha) { if ((rc = ensure(r, r->o_alpha[0], P * 4))) return rc; d_alpha = (float *)r->o_alpha[0].p; }
     }
     if ((rc = ensure(r, r->img_max, (size_t)r->I * 4))) return rc;
+    {   // (bucket, chunk) items of the buckets beyond shared memory: at most one partial chunk per bucket + the full chunks
+        const size_t RTb = (size_t)(r->C + r->I) * r->tile_w * r->tile_h;
+        if ((rc = ensure(r, r->big_items, (RTb + (size_t)(r->max_isects_src / SAS_SORT_CAP3) + 16) * sizeof(int2)))) return rc;
+    }
     // the render before last used this staging set: its D2H copy must have drained before the set is overwritten
     if (async_out && r->async_seq >= 2) SAS_CUDA(r, cudaStreamWaitEvent(st, r->copy_done[set], 0));
     // a blocking host render after async ones reuses staging set 0: wait for the async copy that may still read it
@@ -873,6 +886,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         sas_renderer::GraphKey key;
         memset(&key, 0, sizeof(key));  // padding bytes take part in the memcmp below
         key.I = r->I; key.C = r->C; key.W = r->W; key.H = r->H; key.ns = ns ? 1 : 0; key.flags = sas_variant_flags();
+        key.big = r->big_hint ? 1 : 0;
         for (int k = 0; k < 3; k++) key.bg[k] = out->background[k];
         key.rgb = d_rgb; key.depth = d_depth; key.alpha = d_alpha; key.u8 = d_u8; key.nc = d_nc; key.f16 = d_f16;
         key.max_isects = r->max_isects; key.max_isects_src = r->max_isects_src; key.buf_gen = r->buf_gen;
@@ -954,6 +968,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
             r->async_seq++;
         } else {
             SAS_CUDA(r, cudaStreamSynchronize(st));
+            note_counters(r, r->h_snap->slot[seq & 3ull]);
             if (seq >= r->ovf_floor && r->h_snap->slot[seq & 3ull].overflow) return overflow_error(r, r->h_snap->slot[seq & 3ull], "sas_render");
         }
     }
@@ -969,6 +984,7 @@ int sas_wait_outputs(sas_renderer *r, int age) {
     // the async renders are the last renders issued on this handle unless other modes were mixed in: find the snapshot
     // of this one by its position among ALL renders (async_render_seq remembers the last two)
     const unsigned long long seq = r->async_render_seq[(r->async_seq - 1 - age) & 1u];
+    note_counters(r, r->h_snap->slot[seq & 3ull]);
     if (seq >= r->ovf_floor && r->h_snap->slot[seq & 3ull].overflow) return overflow_error(r, r->h_snap->slot[seq & 3ull], "sas_wait_outputs");
     return SAS_OK;
 }
@@ -985,6 +1001,7 @@ int sas_poll_overflow(sas_renderer *r, long long *need_src, long long *need_all,
     for (unsigned long long k = done > 4 ? done - 4 : 0; k < done; k++) {
         if (k < r->ovf_floor) continue;
         const SasCounters &c = r->h_snap->slot[k & 3ull];
+        note_counters(r, c);
         if (!c.overflow) continue;
         any = 1;
         if ((long long)c.n_isects_src > ns) ns = (long long)c.n_isects_src;
@@ -1021,6 +1038,7 @@ int sas_get_stats(sas_renderer *r, sas_stats *out) {
     SAS_CUDA(r, cudaDeviceSynchronize());
     SasCounters c;
     SAS_CUDA(r, cudaMemcpy(&c, r->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    note_counters(r, c);
     out->n_isects = (int64_t)c.n_isects;
     out->n_isects_src = (int64_t)c.n_isects_src;
     out->n_visible_src = (int64_t)c.n_visible_src;

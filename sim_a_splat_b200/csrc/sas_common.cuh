@@ -124,6 +124,10 @@ struct SasRowSpan {
 #define SAS_SORT_CAP1 2048
 #define SAS_SORT_CAP2 5632
 #define SAS_SORT_CAP3 12288
+// buckets beyond shared memory: more than SAS_BIG_MIN_BUCKET and at most SAS_BIG_MAX_BUCKET entries go through the
+// multi-CTA chunk sort + merge passes (when enabled), the others through the one-CTA global-memory kernel (sas_sort.cu)
+#define SAS_BIG_MIN_BUCKET (4ll * SAS_SORT_CAP3)
+#define SAS_BIG_MAX_BUCKET (64ll * SAS_SORT_CAP3)
 #define SAS_COMP_CLASSES 32
 // Images with at most this many tiles count / reserve bucket slots through per-CTA shared-memory
 // histograms (projection and emission); larger images fall back to global atomics per intersection.
@@ -134,6 +138,9 @@ struct SasWork {
     unsigned sort_count[SAS_SORT_CLASSES], sort_start[SAS_SORT_CLASSES], sort_fill[SAS_SORT_CLASSES], sort_take[SAS_SORT_CLASSES];
     unsigned comp_count[SAS_COMP_CLASSES], comp_start[SAS_COMP_CLASSES], comp_fill[SAS_COMP_CLASSES];
     unsigned comp_total, comp_take;
+    // buckets beyond shared memory (sas_sort.cu): (bucket, chunk) items and one take counter per kernel of the path
+    // ([0] chunk sort, [p] merge pass p)
+    unsigned big_items, big_take[8];
 };
 
 // Sub-tile granularity of the static shortcut: a 16x16 tile is 4 columns (4 px) x 8 rows (2 px) of
@@ -272,7 +279,9 @@ cudaError_t sas_launch_bin_sort(uint2 *pairs, const int *row_tile_offset, const 
 // aux / ev: SAS_SORT_CLASSES - 1 side streams and 2 * SAS_SORT_CLASSES events for the fork / join (may be null: serial)
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
                                  long long capacity, const int *canon_of /*internal -> canonical id of background Gaussians, or null*/,
-                                 int n_bg, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
+                                 int n_bg, int2 *big_items /*[big_items_cap] scratch: (bucket, chunk) of buckets beyond shared memory*/,
+                                 int big_items_cap, int big_on /*enqueue the multi-CTA path for giant buckets*/, cudaStream_t st,
+                                 cudaStream_t *aux, cudaEvent_t *ev, int *n_launches);
 // fill_static: also write the ids of tiles whose link bucket is empty (the compositor never reads those)
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,

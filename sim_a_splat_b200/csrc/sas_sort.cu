@@ -23,6 +23,10 @@
 
 namespace {
 
+// smallest bucket (exclusive) the multi-CTA path takes, from the number of buckets beyond shared memory (n4): with few of
+// them the GPU is idle unless each is spread over many CTAs; with many, one CTA per bucket moves fewer bytes
+__device__ __forceinline__ long long sas_big_min_bucket(unsigned n4) { return n4 < 296u ? (long long)SAS_SORT_CAP3 : SAS_BIG_MIN_BUCKET; }
+
 template <int NT>
 struct alignas(16) SortShared {
     unsigned hist[NT / 32][256];
@@ -179,6 +183,9 @@ __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pair
         if (end > max_isects) end = max_isects;
         const long long nn = end - off;
         if (nn <= 0 || (!IN_GLOBAL && nn > (long long)cap)) continue;
+        // IN_GLOBAL: cap != 0 says the multi-CTA chunk + merge path is on; it takes the buckets of more than
+        // BIG_MIN_BUCKET and at most BIG_MAX_BUCKET entries, this one-CTA kernel the rest
+        if (IN_GLOBAL && cap != 0 && nn > sas_big_min_bucket(n_items) && nn <= SAS_BIG_MAX_BUCKET) continue;
         const int n = (int)nn;
         uint2 *src, *dst;
         if (IN_GLOBAL) {
@@ -207,10 +214,184 @@ __global__ void __launch_bounds__(NT) tile_sort_kernel(uint2 *pairs, uint2 *pair
     }
 }
 
+// ---- buckets beyond shared memory: chunks sorted in shared memory by ALL SMs, then multi-CTA merge passes ---------
+// (round 2; round 1 sorted such a bucket with ONE CTA ping-ponging through global memory, which leaves most of the GPU
+// idle when a small image over a big scene puts every tile in this class.)  A bucket of n > SAS_SORT_CAP3 entries is cut
+// into chunks of SAS_SORT_CAP3; big_plan_kernel lists the (bucket, chunk) items; big_chunk_sort_kernel sorts every chunk
+// like a shared-memory bucket; big_merge_kernel, launched BIG_MAX_PASSES times, merges runs of 2^(p-1) chunks pairwise
+// by merge path, one CTA per output chunk, ping-ponging between `pairs` and `pairs_alt` so that a bucket of P =
+// ceil(log2(chunks)) passes ends in `pairs` (its chunk sort writes into the buffer of the right parity).  Buckets of more
+// than 2^BIG_MAX_PASSES chunks keep the one-CTA kernel.  Everything is device-driven: the launches exist in every step's
+// graph on the big-bucket stream and exit at once when there is nothing to do.
+// Measured (profiles/r02b_big_bucket_sort.txt): a 96x96 view of a 2 M-Gaussian scene (lists up to 155 k entries, 36 tiles)
+// sorts in 0.43 instead of 0.73 ms; but when thousands of buckets of 12-30 k entries already fill every SM (the 6 M-Gaussian
+// 1080p chunk) the one-CTA kernel moves fewer bytes and is faster (17.9 vs 21.8 ms), and the eight extra launches cost
+// ~18 us per step when there is nothing to do.  Hence: when MANY buckets are beyond shared memory (>= 2 per SM: one CTA
+// each already fills the GPU) only those of more than 4 chunks take this path, when few do, all of them
+// (sas_big_min_bucket); and the launches are only enqueued once the renderer has SEEN such lists (sas_api.cu big_hint, from the counters the host
+// reads anyway: stats, overflow polls, the snapshots that travel with host outputs).
+constexpr int BIG_MAX_PASSES = 6;                                   // up to 64 chunks = 786 432 entries per bucket
+constexpr long long BIG_MAX_BUCKET = SAS_BIG_MAX_BUCKET;
+constexpr int BIG_TILE = 2048;                                      // outputs per merge sub-tile (8 per thread, 256 threads)
+
+__device__ __forceinline__ int big_passes(int n_chunks) {
+    int p = 0;
+    while ((1 << p) < n_chunks) p++;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) big_plan_kernel(const int *__restrict__ tile_offset, const int *__restrict__ sort_list, SasWork *work,
+                                                       long long max_isects, int2 *__restrict__ big_items, int items_cap) {
+    const unsigned n4 = work->sort_count[4];
+    const int *list = sort_list + work->sort_start[4];
+    for (unsigned k = blockIdx.x * 256 + threadIdx.x; k < n4; k += gridDim.x * 256) {
+        const int b = list[k];
+        long long off = tile_offset[b], end = tile_offset[b + 1];
+        if (off < 0 || end < off) continue;
+        if (end > max_isects) end = max_isects;
+        const long long n = end - off;
+        if (n <= sas_big_min_bucket(n4) || n > BIG_MAX_BUCKET) continue;
+        const int nc = (int)((n + SAS_SORT_CAP3 - 1) / SAS_SORT_CAP3);
+        const unsigned base = atomicAdd(&work->big_items, (unsigned)nc);
+        for (int c = 0; c < nc; c++)
+            if (base + c < (unsigned)items_cap) big_items[base + c] = make_int2(b, c);
+    }
+}
+
+// bucket b -> (offset, entries, chunks, passes); false if the bucket is not handled by this path
+__device__ __forceinline__ bool big_bucket(const int *__restrict__ tile_offset, int b, long long max_isects, unsigned n4, long long &off, int &n,
+                                           int &nc, int &P) {
+    off = tile_offset[b];
+    long long end = tile_offset[b + 1];
+    if (off < 0 || end < off) return false;
+    if (end > max_isects) end = max_isects;
+    const long long nn = end - off;
+    if (nn <= sas_big_min_bucket(n4) || nn > BIG_MAX_BUCKET) return false;
+    n = (int)nn;
+    nc = (n + SAS_SORT_CAP3 - 1) / SAS_SORT_CAP3;
+    P = big_passes(nc);
+    return true;
+}
+
+__global__ void __launch_bounds__(512) big_chunk_sort_kernel(uint2 *pairs, uint2 *pairs_alt, const int *__restrict__ tile_offset,
+                                                             const int2 *__restrict__ big_items, int items_cap, SasWork *work,
+                                                             long long max_isects, const int *__restrict__ canon_of, int n_bg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortShared<512> &sh = *reinterpret_cast<SortShared<512> *>(smem_raw);
+    __shared__ unsigned s_take;
+    const unsigned n_items = min(work->big_items, (unsigned)items_cap);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_take = atomicAdd(&work->big_take[0], 1u);
+        __syncthreads();
+        const unsigned k = s_take;
+        if (k >= n_items) break;
+        const int2 it = big_items[k];
+        long long off; int nb_, nc, P;
+        if (!big_bucket(tile_offset, it.x, max_isects, work->sort_count[4], off, nb_, nc, P)) continue;
+        const int c0 = it.y * SAS_SORT_CAP3, n = min(SAS_SORT_CAP3, nb_ - c0);
+        uint2 *src = reinterpret_cast<uint2 *>(smem_raw + sizeof(SortShared<512>)), *dst = src + SAS_SORT_CAP3;
+        for (int i = threadIdx.x; i < n; i += 512) src[i] = pairs[off + c0 + i];
+        __syncthreads();
+        if (n > 1) {
+#pragma unroll 1
+            for (int shift = 0; shift < 32; shift += 8) {
+                if (radix_pass(src, dst, n, shift, sh)) {
+                    uint2 *t = src; src = dst; dst = t;
+                }
+            }
+            if (fix_ties<512>(src, dst, n, canon_of, n_bg)) {
+                uint2 *t = src; src = dst; dst = t;
+            }
+        }
+        uint2 *out = ((P & 1) ? pairs_alt : pairs) + off + c0;  // P more buffer flips follow: an even number ends in `pairs`
+        for (int i = threadIdx.x; i < n; i += 512) out[i] = src[i];
+    }
+}
+
+// 64-bit merge key: depth bits, then the CANONICAL Gaussian id (the order a stable sort of ascending emission gives)
+__device__ __forceinline__ unsigned long long big_key(const uint2 e, const int *__restrict__ canon_of, int n_bg) {
+    const unsigned id = (canon_of && (int)e.y < n_bg) ? (unsigned)__ldg(canon_of + e.y) : e.y;
+    return ((unsigned long long)e.x << 32) | id;
+}
+
+__global__ void __launch_bounds__(256) big_merge_kernel(uint2 *pairs, uint2 *pairs_alt, const int *__restrict__ tile_offset,
+                                                        const int2 *__restrict__ big_items, int items_cap, SasWork *work, int pass,
+                                                        long long max_isects, const int *__restrict__ canon_of, int n_bg) {
+    __shared__ uint2 sab[BIG_TILE], so[BIG_TILE];  // the two input windows of a sub-tile share sab: wa + wb = its outputs
+    __shared__ unsigned s_take;
+    __shared__ int s_split[2];
+    const unsigned n_items = min(work->big_items, (unsigned)items_cap);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_take = atomicAdd(&work->big_take[pass], 1u);
+        __syncthreads();
+        const unsigned k = s_take;
+        if (k >= n_items) break;
+        const int2 it = big_items[k];
+        long long off; int n, nc, P;
+        if (!big_bucket(tile_offset, it.x, max_isects, work->sort_count[4], off, n, nc, P)) continue;
+        if (pass > P) continue;  // this bucket is finished
+        // after pass q the bucket lives in `pairs` iff (P - q) is even
+        const uint2 *src = (((P - (pass - 1)) & 1) ? pairs_alt : pairs) + off;
+        uint2 *dst = (((P - pass) & 1) ? pairs_alt : pairs) + off;
+        const long long half = (long long)SAS_SORT_CAP3 << (pass - 1), pairlen = 2 * half;
+        const long long o0 = (long long)it.y * SAS_SORT_CAP3;               // first output position of this item in the bucket
+        const long long A0 = (o0 / pairlen) * pairlen;                       // start of the pair of runs it belongs to
+        const int na = (int)min(half, (long long)n - A0);
+        const long long B0 = A0 + half;
+        const int nb = (int)max(0ll, min(half, (long long)n - B0));
+        const int d_lo = (int)(o0 - A0), d_hi = (int)min((long long)d_lo + SAS_SORT_CAP3, (long long)na + nb);
+        const uint2 *A = src + A0, *B = src + B0;
+        if (nb == 0) {  // an unpaired run at the end of the bucket: carried over to the other buffer
+            for (int d = d_lo + threadIdx.x; d < d_hi; d += 256) dst[A0 + d] = A[d];
+            continue;
+        }
+        for (int d0 = d_lo; d0 < d_hi; d0 += BIG_TILE) {
+            const int cnt = min(BIG_TILE, d_hi - d0);
+            __syncthreads();
+            if (threadIdx.x < 2) {  // merge-path split of the sub-tile's two ends: entries of A among the first d merged entries
+                const int d = threadIdx.x == 0 ? d0 : d0 + cnt;
+                int lo = max(0, d - nb), hi = min(d, na);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (big_key(A[mid], canon_of, n_bg) <= big_key(B[d - 1 - mid], canon_of, n_bg)) lo = mid + 1; else hi = mid;
+                }
+                s_split[threadIdx.x] = lo;
+            }
+            __syncthreads();
+            const int a0 = s_split[0], wa = s_split[1] - a0, b0 = d0 - a0, wb = cnt - wa;
+            uint2 *sa = sab, *sb = sab + wa;
+            for (int i = threadIdx.x; i < wa; i += 256) sa[i] = A[a0 + i];
+            for (int i = threadIdx.x; i < wb; i += 256) sb[i] = B[b0 + i];
+            __syncthreads();
+            const int t0 = threadIdx.x * 8;
+            if (t0 < cnt) {
+                int lo = max(0, t0 - wb), hi = min(t0, wa);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (big_key(sa[mid], canon_of, n_bg) <= big_key(sb[t0 - 1 - mid], canon_of, n_bg)) lo = mid + 1; else hi = mid;
+                }
+                int ia = lo, ib = t0 - lo;
+#pragma unroll
+                for (int v = 0; v < 8; v++)
+                    if (t0 + v < cnt) {
+                        const bool take_a = ib >= wb || (ia < wa && big_key(sa[ia], canon_of, n_bg) <= big_key(sb[ib], canon_of, n_bg));
+                        so[t0 + v] = take_a ? sa[ia] : sb[ib];
+                        if (take_a) ia++; else ib++;
+                    }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt; i += 256) dst[A0 + d0 + i] = so[i];
+        }
+    }
+}
+
 template <int NT>
 size_t sort_smem(int cap) { return sizeof(SortShared<NT>) + 2 * (size_t)cap * sizeof(uint2); }
 
 int g_sort_sms = 148;
+int g_sort_big = 1;    // SAS_SORT_BIG=0: buckets beyond shared memory on one CTA each (round 1), no chunk + merge path
 int g_sort_radix = 1;  // SAS_SORT=bin: the bin sort of sas_binsort.cu for the shared-memory classes (measured slower, see there); default: LSD radix
 
 }  // namespace
@@ -218,7 +399,10 @@ int g_sort_radix = 1;  // SAS_SORT=bin: the bin sort of sas_binsort.cu for the s
 cudaError_t sas_sort_init(int n_sms) {
     g_sort_sms = n_sms > 0 ? n_sms : 148;
     if (const char *ev = getenv("SAS_SORT")) g_sort_radix = (ev[0] != 'b');
+    if (const char *ev = getenv("SAS_SORT_BIG")) g_sort_big = atoi(ev) != 0;
     cudaError_t e = sas_binsort_init();
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(big_chunk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem<512>(SAS_SORT_CAP3));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tile_sort_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sort_smem<512>(SAS_SORT_CAP3));
@@ -229,12 +413,20 @@ cudaError_t sas_sort_init(int n_sms) {
 // (fork on an event of the caller's stream, join back into it): the step pays for the slowest class
 // instead of the sum of five partially filled launches.
 cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_tile_offset, const int *sort_list, SasWork *work,
-                                 long long capacity, const int *canon_of, int n_bg, cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev,
-                                 int *n_launches) {
+                                 long long capacity, const int *canon_of, int n_bg, int2 *big_items, int big_items_cap, int big_on,
+                                 cudaStream_t st, cudaStream_t *aux, cudaEvent_t *ev, int *n_launches) {
     // grid = SMs x resident CTAs of the class (threads / shared memory bound)
     const int sms = g_sort_sms;
     const bool fork = aux != nullptr && ev != nullptr && (sas_variant_flags() & 4);
     cudaError_t e;
+    // giant buckets first, while every SM is free: the chunk sort needs a whole SM's shared memory per CTA and would
+    // otherwise queue behind the other classes' CTAs
+    const bool big = big_on && big_items != nullptr && big_items_cap > 0 && g_sort_big;
+    if (big) {
+        big_plan_kernel<<<8, 256, 0, st>>>(row_tile_offset, sort_list, work, capacity, big_items, big_items_cap);
+        big_chunk_sort_kernel<<<sms, 512, sort_smem<512>(SAS_SORT_CAP3), st>>>(pairs, pairs_alt, row_tile_offset, big_items, big_items_cap, work,
+                                                                            capacity, canon_of, n_bg);
+    }
     if (fork && (e = cudaEventRecord(ev[0], st)) != cudaSuccess) return e;
     // class -> stream: the class with the longest critical path (<= 5632 entries, two CTAs per SM) stays on the caller's stream
     cudaStream_t s_of[SAS_SORT_CLASSES] = {st, st, st, st, st};
@@ -258,8 +450,16 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
                                                                                           SAS_SORT_CAP0, capacity, canon_of, n_bg);
     }
     // buckets beyond shared memory: 32 warps per CTA (measured on the 6 M-Gaussian 1080p chunk: sort 26.5 -> 19.5 ms)
-    tile_sort_kernel<1024, true><<<sms, 1024, sizeof(SortShared<1024>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4, 0,
-                                                                                  capacity, canon_of, n_bg);
+    if (big) {
+        for (int p = 1; p <= BIG_MAX_PASSES; p++)
+            big_merge_kernel<<<sms * 2, 256, 0, s_of[4]>>>(pairs, pairs_alt, row_tile_offset, big_items, big_items_cap, work, p, capacity, canon_of,
+                                                          n_bg);
+        if (n_launches) *n_launches += 2 + BIG_MAX_PASSES;
+    }
+    // one CTA per bucket through global memory: every bucket beyond shared memory when the multi-CTA path is off, else
+    // those it leaves (at most BIG_MIN_BUCKET or more than BIG_MAX_BUCKET entries)
+    tile_sort_kernel<1024, true><<<sms, 1024, sizeof(SortShared<1024>), s_of[4]>>>(pairs, pairs_alt, row_tile_offset, sort_list, work, 4,
+                                                                                  big ? 1 : 0, capacity, canon_of, n_bg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (fork)
         for (int k = 0; k < 4; k++) {

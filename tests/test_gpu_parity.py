@@ -148,6 +148,41 @@ def test_bucket_sort_size_classes_and_depth_ties():
     assert gpu["stats"]["max_tile_list"] == counts.max()
 
 
+def test_giant_buckets_chunk_sort_and_merge_passes():
+    """Buckets far beyond shared memory (round 2: chunks sorted in shared memory by all SMs + multi-CTA merge-path passes,
+    csrc/sas_sort.cu big_*): tile lists of 85 000 and 205 300 entries = 7 and 17 chunks (3 and 5 merge passes, odd run
+    counts, both ping-pong parities), half of the entries in equal-depth runs that straddle chunks -- the merge orders
+    ties by Gaussian id."""
+    sizes = (30000, 55000, 150000)
+    sc = _cluster_scene(sizes, seed=12, spread=0.003, opacity=0.004)
+    # more ties, far apart in emission order: the last 2000 Gaussians are exact copies of 2000 of the big cluster
+    n0 = sizes[0] + sizes[1]
+    for arr in (sc.means, sc.quats, sc.scales, sc.opacities, sc.sh):
+        arr[-2000:] = arr[n0 + 1000:n0 + 3000]
+    W, H = 192, 48
+    vm = S.lookat_viewmat((0.0, -2.5, 0.0), (-0.2, 0.0, 0.0))
+    K = S.fov_intrinsics(W, H, 40.0)
+    r = SplatRenderer(sc, max_images=1, max_width=W, max_height=H, max_isects=2_000_000)
+    # the path's launches are only enqueued once the renderer has SEEN such lists (a host-side hint from the counters):
+    # the first checked render goes through the one-CTA kernel and sets it ...
+    r.set_cameras(vm[None], K, W, H)
+    first = {k: v.clone() for k, v in r.render(("rgb", "n_contrib")).items()}
+    n0 = r.last_launch_count()
+    # ... the second one (what run_both compares with the oracle) takes the chunk sort + merge passes
+    gpu, ref = run_both(sc, vm[None], K[None], W, H, renderer=r)
+    assert r.last_launch_count() == n0 + 8           # plan + chunk sort + 6 merge passes
+    counts = np.diff(np.append(ref["isect_offsets"].ravel(), ref["M"]))
+    assert counts.max() > 12 * 12288 and np.sum(counts > 4 * 12288) >= 2
+    assert np.sum(np.diff(ref["isect_ids"]) == 0) >= 2000
+    rep = compare(gpu, ref)
+    print(rep, sorted(counts)[-4:])
+    assert_parity(rep)
+    assert gpu["stats"]["max_tile_list"] == counts.max()
+    np.testing.assert_array_equal(first["n_contrib"].cpu().numpy(), gpu["n_contrib"])   # both sort paths agree
+    np.testing.assert_array_equal(first["rgb"].cpu().numpy(), gpu["rgb"])
+    r.close()
+
+
 def test_rendering_is_deterministic_and_host_path_matches():
     sc = S.make_synthetic_scene(20000, 2, seed=13, link_counts=(900, 500))
     W, H = 160, 128
