@@ -39,6 +39,9 @@ def test_sass_is_sm100a_and_uses_async_copies():
     sass = subprocess.run(["cuobjdump", "-sass", str(_build.LIB)], capture_output=True, text=True).stdout
     assert "LDGSTS" in sass  # cp.async staging in the compositor
     assert "VOTE" in sass and "ATOMS" in sass  # ballot multi-split / shared-memory histograms in the bucket sort
+    # the bulk-async staging variant of the compositor (SAS_VARIANT bit 11: cp.async.bulk + mbarrier expect_tx) is in the
+    # binary too -- measured slower than LDGSTS for this 48-byte gather, profiles/r02b_bulk_staging.txt
+    assert "UBLKCP" in sass and "SYNCS" in sass
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -70,6 +73,33 @@ def test_entry_points_reject_null_handles_without_touching_a_device():
     assert lib.sas_wait_outputs(None, 0) == -1          # SAS_EINVAL
     assert lib.sas_render(None, None, None) == -1
     assert lib.sas_last_launch_count(None) == 0
+    assert lib.sas_reserve_isects2(None, 1, 1) == -1
+    assert lib.sas_poll_overflow(None, None, None, None) == -1
+    assert lib.sas_set_fk_model(None, None) == -1
+    assert lib.sas_set_link_poses_from_joints(None, None, 1, None, 0, None) == -1
+
+
+def test_packed_layout_is_pure_host_arithmetic():
+    """sas_packed_layout: the one-block layout of the host outputs (no device involved): outputs in SAS_OUT_* bit order, every
+    offset 256-byte aligned, unwanted outputs untouched."""
+    lib = _lib.load()
+    offs = (C.c_size_t * 6)(*([12345] * 6))
+    total = C.c_size_t()
+    I, W, H = 256, 96, 96
+    P = I * W * H
+    want = 1 | 4                                          # uint8 RGB + f32 depth: the bench's end-to-end observation
+    assert lib.sas_packed_layout(I, W, H, want, offs, C.byref(total)) == 0
+    assert offs[0] == 0 and offs[2] == ((3 * P + 255) // 256) * 256 and offs[1] == 12345 and offs[3] == 12345
+    assert total.value == offs[2] + ((4 * P + 255) // 256) * 256
+    assert lib.sas_packed_layout(I, W, H, 63, offs, C.byref(total)) == 0
+    sizes = [3, 2, 4, 4, 12, 4]
+    for k in range(6):
+        assert offs[k] % 256 == 0
+        if k:
+            assert offs[k] >= offs[k - 1] + sizes[k - 1] * P
+    assert total.value >= offs[5] + 4 * P
+    assert lib.sas_packed_layout(0, W, H, 1, offs, C.byref(total)) == -1
+    assert lib.sas_packed_layout(I, W, H, 64, offs, C.byref(total)) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
