@@ -224,6 +224,19 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bin
 constexpr int MERGE_THREADS = 128;
 constexpr int MERGE_VT = 8;
 constexpr int MERGE_CHUNK = MERGE_THREADS * MERGE_VT;
+
+// Ablation knob (SAS_COMPACT_MAX, default 32 = every dynamic tile): compact only the tiles whose link Gaussians reach at
+// most this many of the 32 pixel groups.  Measured (profiles/r02b_compact_lists.txt): most of the saving is in the tiles
+// with 29..32 groups reached -- they are also the longest lists -- so the gate stays open.
+static int compact_max_groups() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SAS_COMPACT_MAX");
+        v = e ? atoi(e) : 32;
+        if (v < 0 || v > 32) v = 32;
+    }
+    return v;
+}
 constexpr int MERGE_MAX_SPLITS = 64;  // chunk boundaries resolved per round
 
 // number of background entries among the first d merged entries
@@ -237,14 +250,45 @@ __device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB ke
     return lo;
 }
 
+// bg_reach_kernel: for every entry of the VIEW buckets (background Gaussians, sorted) the 32-bit mask of the tile's 4x2
+// groups its culling box reaches -- the same mask the compositor computes when it stages the record, but it does not
+// depend on the env, so it is computed once per view entry.  The merge uses it to COMPACT the lists it hands to the
+// compositor: a background record that reaches none of the groups an image tile's link Gaussians can reach cannot touch
+// a pixel composited from that list (the other groups are copied from the view tile), so it is left out -- 28 % of the
+// records of the pusht batch's dynamic tiles.  gridDim.y CTAs per (view, tile) bucket, each a slice of its entries.
+__global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
+                                                       const SasRecord *__restrict__ rec, int n_bg, int T, int tile_w, long long cap_src,
+                                                       unsigned *__restrict__ bg_reach) {
+    const int vt = blockIdx.x, v = vt / T, t = vt - v * T;
+    const int ty = t / tile_w, tx = t - ty * tile_w;
+    long long off = row_tile_offset[vt], end = row_tile_offset[vt + 1];
+    if (off < 0 || end < off) return;
+    if (end > cap_src) end = cap_src;
+    const SasRecord *rb = rec + (size_t)v * n_bg;
+    const long long slice = (end - off + gridDim.y - 1) / gridDim.y;
+    off += slice * blockIdx.y;
+    if (off + slice < end) end = off + slice;
+    for (long long k = off + threadIdx.x; k < end; k += 256) {
+        const SasRecord *r = rb + pairs[k].y;
+        const float4 A = r->a, B = r->b;
+        bg_reach[k] = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+    }
+}
+
+// bg_reach / tile_dyn_mask / comp_len (all or none): compact the merged list of every image tile to the records the
+// compositor needs (see bg_reach_kernel) and store its length; the ids stay in merged order at the tile's offset.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                               const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
                                                               int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all,
                                                               int fill_static, const int *__restrict__ comp_list,
-                                                              const SasWork *__restrict__ work, int I) {
+                                                              const SasWork *__restrict__ work, int I, const unsigned *__restrict__ bg_reach,
+                                                              const unsigned *__restrict__ tile_dyn_mask, int *__restrict__ comp_len,
+                                                              int compact_max_groups) {
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
+    __shared__ unsigned sr[MERGE_CHUNK];
     __shared__ int s_out[MERGE_CHUNK];
     __shared__ int s_split[MERGE_MAX_SPLITS + 1];
+    __shared__ int s_wsum[MERGE_THREADS / 32];
     int t, i;
     if (comp_list) {
         // render path: CTA k takes entry k of the compositor's work list -- exactly the (image, tile) lists that need
@@ -267,14 +311,21 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
     if (nb == 0 && !fill_static) return;  // composited from the view's bucket; ids only needed by debug fetches
     const uint2 *bgp = pairs + b0, *dyp = pairs + d0;
     const int n = na + nb;
+    const bool has_len = comp_len != nullptr && bg_reach != nullptr && tile_dyn_mask != nullptr;
     if (nb == 0 || na == 0) {  // only one list (a static tile, or no background here): plain copy
         const uint2 *src = nb == 0 ? bgp : dyp;
         for (int k = threadIdx.x; k < n; k += MERGE_THREADS) {
             const long long pos = o0 + k;
             if (pos < cap_all) merged[pos] = (int)src[k].y;
         }
+        if (has_len && threadIdx.x == 0) comp_len[(size_t)i * T + t] = n;
         return;
     }
+    const unsigned dyn = has_len ? tile_dyn_mask[(size_t)i * T + t] : 0xffffffffu;
+    // a tile whose link Gaussians reach (nearly) every group drops (nearly) nothing: plain merge, full length
+    const bool compact = has_len && __popc(dyn) <= compact_max_groups;
+    const unsigned *brp = compact ? bg_reach + b0 : nullptr;
+    long long o_run = o0;  // compaction: where the next chunk's kept ids go
     const int n_chunks = (n + MERGE_CHUNK - 1) / MERGE_CHUNK;
     for (int cr = 0; cr < n_chunks; cr += MERGE_MAX_SPLITS) {  // rounds of up to MERGE_MAX_SPLITS chunks
         __syncthreads();
@@ -290,27 +341,64 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
             const int wa = a1 - a0, wb = cn - wa, bst = c0 - a0;
             for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sa[k] = bgp[a0 + k];
             for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[bst + k];
+            if (compact)
+                for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sr[k] = brp[a0 + k];
             __syncthreads();
             const int d = threadIdx.x * MERGE_VT;
+            int ids[MERGE_VT];
+            unsigned keep = 0u;  // bit v: output d + v exists and is kept
             if (d < cn) {
                 int ia = merge_path(d, wa, wb, [&](int k) { return sa[k].x; }, [&](int k) { return sb[k].x; });
                 int ib = d - ia;
 #pragma unroll
                 for (int v = 0; v < MERGE_VT; v++) {
+                    ids[v] = 0;
                     if (d + v < cn) {
                         const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
-                        s_out[d + v] = (int)(take_a ? sa[ia].y : sb[ib].y);
+                        ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
+                        // a background record that reaches none of the groups the link Gaussians can reach is not needed
+                        if (!compact || !take_a || (sr[ia] & dyn) != 0u) keep |= 1u << v;
                         if (take_a) ia++; else ib++;
                     }
                 }
             }
+            int cn_out = cn;
+            if (!compact) {
+#pragma unroll
+                for (int v = 0; v < MERGE_VT; v++)
+                    if (keep & (1u << v)) s_out[d + v] = ids[v];
+            } else {  // exclusive scan of the kept counts over the CTA, then every thread writes its kept ids densely
+                const int cnt = __popc(keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                int inc = cnt;
+#pragma unroll
+                for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                    const int tt = __shfl_up_sync(0xffffffffu, inc, s_);
+                    if (lane >= s_) inc += tt;
+                }
+                if (lane == 31) s_wsum[warp] = inc;
+                __syncthreads();
+                int pre = 0, tot = 0;
+#pragma unroll
+                for (int w = 0; w < MERGE_THREADS / 32; w++) {
+                    const int sw = s_wsum[w];
+                    if (w < warp) pre += sw;
+                    tot += sw;
+                }
+                int pos = pre + inc - cnt;
+#pragma unroll
+                for (int v = 0; v < MERGE_VT; v++)
+                    if (keep & (1u << v)) s_out[pos++] = ids[v];
+                cn_out = tot;
+            }
             __syncthreads();
-            for (int k = threadIdx.x; k < cn; k += MERGE_THREADS) {  // coalesced write-out
-                const long long pos = o0 + c0 + k;
+            for (int k = threadIdx.x; k < cn_out; k += MERGE_THREADS) {  // coalesced write-out
+                const long long pos = o_run + k;
                 if (pos < cap_all) merged[pos] = s_out[k];
             }
+            o_run += cn_out;
         }
     }
+    if (has_len && threadIdx.x == 0) comp_len[(size_t)i * T + t] = (int)(o_run - o0);
 }
 
 }  // namespace
@@ -340,18 +428,30 @@ cudaError_t sas_bin_init() {
     return cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SAS_SMEM_TILES_MAX * (int)sizeof(unsigned int));
 }
 
+cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
+                                long long cap_src, unsigned *bg_reach, cudaStream_t st) {
+    if (C <= 0 || T <= 0) return cudaSuccess;
+    // a handful of views x tiles: cut every bucket into slices so that the kernel fills the GPU (36 buckets on the pusht batch)
+    const long long buckets = (long long)C * T;
+    const unsigned slices = buckets >= 2048 ? 1u : buckets >= 512 ? 4u : 16u;
+    bg_reach_kernel<<<dim3((unsigned)buckets, slices), 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, T, tile_w, cap_src, bg_reach);
+    return cudaGetLastError();
+}
+
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
-                             const int *comp_list, const SasWork *work, cudaStream_t st) {
+                             const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
+                             int *comp_len, cudaStream_t st) {
     static int lpt = -1;  // SAS_MERGE_LPT=0: one CTA per (tile, image) in grid order, as for debug fetches
     if (lpt < 0) { const char *e = getenv("SAS_MERGE_LPT"); lpt = e ? atoi(e) : 1; }
     if (comp_list && work && !fill_static && lpt) {
         merge_kernel<<<(unsigned)((long long)(I + C) * T), MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T,
-                                                                                 merged_gid, cap_src, cap_all, 0, comp_list, work, I);
+                                                                                 merged_gid, cap_src, cap_all, 0, comp_list, work, I, bg_reach,
+                                                                                 tile_dyn_mask, comp_len, compact_max_groups());
     } else {
         dim3 grid(T, I);
         merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
-                                                     cap_all, fill_static, nullptr, nullptr, I);
+                                                     cap_all, fill_static, nullptr, nullptr, I, nullptr, nullptr, nullptr, 32);
     }
     return cudaGetLastError();
 }
