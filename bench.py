@@ -332,9 +332,12 @@ def run_ours(args):
             t0 = time.perf_counter()
             tickets = []
             o = None
+            issue_s = 0.0   # host time spent issuing (pose upload + render_async), i.e. not waiting for observations
             for i in range(args.steps):
+                ti = time.perf_counter()
                 pr.set_link_poses(poses_pin[i % len(poses_pin)].numpy())
                 tickets.append(pr.render_async(out_names))
+                issue_s += time.perf_counter() - ti
                 if i >= 2:
                     o = pr.wait(tickets[i - 2])  # consume step i-2 while i-1 and i are on the device: a handle's next render
                                                  # is already queued behind its current one when that one's copy is waited for
@@ -342,10 +345,10 @@ def run_ours(args):
                 o = pr.wait(tk)
             dt = (time.perf_counter() - t0) * 1e3
             barrier()
-            return dt, o
+            return dt, o, issue_s * 1e3 / args.steps
 
-        ms_e2e, obs = e2e_pipelined(e2e_names)
-        ms_e2e_f16, obs16 = e2e_pipelined(("rgb_u8", "depth_f16"))   # 5 B/px instead of 7
+        ms_e2e, obs, ms_issue = e2e_pipelined(e2e_names)
+        ms_e2e_f16, obs16, _ = e2e_pipelined(("rgb_u8", "depth_f16"))   # 5 B/px instead of 7
         # (c) observations handed over as CUDA tensors (an on-device policy): H2D poses every step, no D2H
         for i in range(3):
             pr.set_link_poses(poses_pin[i % len(poses_pin)].numpy()); pr.render(e2e_names)
@@ -456,6 +459,7 @@ def run_ours(args):
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(pose_sets[0].nbytes), "d2h_bytes_per_step": int(I * H * W * (3 + 4)),
                     "outputs": "uint8 RGB [I,H,W,3] + f32 depth [I,H,W] into ONE pinned host block, one cudaMemcpyAsync per step",
+                    "host_issue_ms_per_step": round(ms_issue, 4),   # rank 0's host time inside set_link_poses + render_async (the rest of a step it waits)
                     "mode": "PipelinedSplatRenderer.render_async / wait (two libsas handles on two streams, sas_render mem=HOST_ASYNC + "
                             "sas_wait_outputs): two steps on the device, the host consumes step k-2 after issuing step k; step k+1's "
                             "projection/sort overlaps step k's compositing tail and step k-1's D2H; host wall clock, max over ranks",

@@ -215,11 +215,11 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint2 *__restrict__ bin
 // sorted link bucket, by depth bits, background first on ties (background ids are the lower ones in
 // canonical order, so this is the order a stable sort of gsplat's keys gives).
 //
-// Merge-path: one CTA per (image, tile).  The output is cut into chunks of 1024 ids; the split of
-// every chunk boundary (how many background entries precede it) is found up front by one thread per
-// boundary with a binary search over the two global lists; per chunk the two key/id windows are
-// staged in shared memory, every thread finds the split of its own 8-id diagonal with a search in
-// shared memory and merges 8 ids sequentially, writing 32 contiguous bytes.  Tiles whose link
+// Merge-path: one CTA per (image, tile).  The output is cut into chunks of 1024 ids which the CTA
+// produces in order: per chunk the next (up to) 1024 entries of BOTH lists are staged in shared
+// memory (where the chunk starts in either list is known from the previous chunk), every thread
+// finds the split of its own 8-id diagonal with a search in shared memory and merges 8 ids
+// sequentially, and the ids leave through shared memory in coalesced rows.  Tiles whose link
 // bucket is empty are skipped (the compositor takes them from the view's bucket) unless fill_static.
 constexpr int MERGE_THREADS = 128;
 constexpr int MERGE_VT = 8;
@@ -237,7 +237,6 @@ static int compact_max_groups() {
     }
     return v;
 }
-constexpr int MERGE_MAX_SPLITS = 64;  // chunk boundaries resolved per round
 
 // number of background entries among the first d merged entries
 template <typename KA, typename KB>
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
     __shared__ unsigned sr[MERGE_CHUNK];
     __shared__ int s_out[MERGE_CHUNK];
-    __shared__ int s_split[MERGE_MAX_SPLITS + 1];
+    __shared__ int s_used;
     __shared__ int s_wsum[MERGE_THREADS / 32];
     int t, i;
     if (comp_list) {
@@ -326,77 +325,78 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
     const bool compact = has_len && __popc(dyn) <= compact_max_groups;
     const unsigned *brp = compact ? bg_reach + b0 : nullptr;
     long long o_run = o0;  // compaction: where the next chunk's kept ids go
+    // Streaming merge: the CTA walks the tile's chunks in order, so it knows where chunk c starts in both lists once
+    // chunk c-1 is merged -- no merge-path split search over global memory (a dozen dependent L2 round trips per tile,
+    // more than half of a CTA's life in round 1's kernel).  A chunk of cn outputs takes at most cn entries of either
+    // list: both windows are loaded (coalesced; the unused tail is loaded again by the next chunk) and the merge path
+    // is resolved in shared memory only.
     const int n_chunks = (n + MERGE_CHUNK - 1) / MERGE_CHUNK;
-    for (int cr = 0; cr < n_chunks; cr += MERGE_MAX_SPLITS) {  // rounds of up to MERGE_MAX_SPLITS chunks
+    int a_pos = 0, b_pos = 0;  // entries of either list consumed so far
+    for (int c = 0; c < n_chunks; c++) {
+        const int cn = min(MERGE_CHUNK, n - c * MERGE_CHUNK);
+        const int wa = min(cn, na - a_pos), wb = min(cn, nb - b_pos);
+        __syncthreads();  // the previous chunk's readers of sa / sb / s_out / s_used are done
+        for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sa[k] = bgp[a_pos + k];
+        for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[b_pos + k];
+        if (compact)
+            for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sr[k] = brp[a_pos + k];
         __syncthreads();
-        if (threadIdx.x <= MERGE_MAX_SPLITS && cr + (int)threadIdx.x <= n_chunks) {
-            const int d = min(n, (cr + (int)threadIdx.x) * MERGE_CHUNK);
-            s_split[threadIdx.x] = merge_path(d, na, nb, [&](int k) { return __ldg(&bgp[k].x); }, [&](int k) { return __ldg(&dyp[k].x); });
+        const int d = threadIdx.x * MERGE_VT;
+        int ids[MERGE_VT];
+        unsigned keep = 0u;  // bit v: output d + v exists and is kept
+        if (d < cn) {
+            int ia = merge_path(d, wa, wb, [&](int k) { return sa[k].x; }, [&](int k) { return sb[k].x; });
+            int ib = d - ia;
+#pragma unroll
+            for (int v = 0; v < MERGE_VT; v++) {
+                ids[v] = 0;
+                if (d + v < cn) {
+                    const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
+                    ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
+                    // a background record that reaches none of the groups the link Gaussians can reach is not needed
+                    if (!compact || !take_a || (sr[ia] & dyn) != 0u) keep |= 1u << v;
+                    if (take_a) ia++; else ib++;
+                }
+            }
+            if (d + MERGE_VT >= cn) s_used = ia;  // the thread that merges the chunk's last output: background entries used
+        }
+        int cn_out = cn;
+        if (!compact) {
+#pragma unroll
+            for (int v = 0; v < MERGE_VT; v++)
+                if (keep & (1u << v)) s_out[d + v] = ids[v];
+        } else {  // exclusive scan of the kept counts over the CTA, then every thread writes its kept ids densely
+            const int cnt = __popc(keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            int inc = cnt;
+#pragma unroll
+            for (int s_ = 1; s_ < 32; s_ <<= 1) {
+                const int tt = __shfl_up_sync(0xffffffffu, inc, s_);
+                if (lane >= s_) inc += tt;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < MERGE_THREADS / 32; w++) {
+                const int sw = s_wsum[w];
+                if (w < warp) pre += sw;
+                tot += sw;
+            }
+            int pos = pre + inc - cnt;
+#pragma unroll
+            for (int v = 0; v < MERGE_VT; v++)
+                if (keep & (1u << v)) s_out[pos++] = ids[v];
+            cn_out = tot;
         }
         __syncthreads();
-        const int c_end = min(n_chunks, cr + MERGE_MAX_SPLITS);
-        for (int c = cr; c < c_end; c++) {
-            const int c0 = c * MERGE_CHUNK, cn = min(MERGE_CHUNK, n - c0);
-            const int a0 = s_split[c - cr], a1 = s_split[c - cr + 1];
-            const int wa = a1 - a0, wb = cn - wa, bst = c0 - a0;
-            for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sa[k] = bgp[a0 + k];
-            for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[bst + k];
-            if (compact)
-                for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sr[k] = brp[a0 + k];
-            __syncthreads();
-            const int d = threadIdx.x * MERGE_VT;
-            int ids[MERGE_VT];
-            unsigned keep = 0u;  // bit v: output d + v exists and is kept
-            if (d < cn) {
-                int ia = merge_path(d, wa, wb, [&](int k) { return sa[k].x; }, [&](int k) { return sb[k].x; });
-                int ib = d - ia;
-#pragma unroll
-                for (int v = 0; v < MERGE_VT; v++) {
-                    ids[v] = 0;
-                    if (d + v < cn) {
-                        const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
-                        ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
-                        // a background record that reaches none of the groups the link Gaussians can reach is not needed
-                        if (!compact || !take_a || (sr[ia] & dyn) != 0u) keep |= 1u << v;
-                        if (take_a) ia++; else ib++;
-                    }
-                }
-            }
-            int cn_out = cn;
-            if (!compact) {
-#pragma unroll
-                for (int v = 0; v < MERGE_VT; v++)
-                    if (keep & (1u << v)) s_out[d + v] = ids[v];
-            } else {  // exclusive scan of the kept counts over the CTA, then every thread writes its kept ids densely
-                const int cnt = __popc(keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-                int inc = cnt;
-#pragma unroll
-                for (int s_ = 1; s_ < 32; s_ <<= 1) {
-                    const int tt = __shfl_up_sync(0xffffffffu, inc, s_);
-                    if (lane >= s_) inc += tt;
-                }
-                if (lane == 31) s_wsum[warp] = inc;
-                __syncthreads();
-                int pre = 0, tot = 0;
-#pragma unroll
-                for (int w = 0; w < MERGE_THREADS / 32; w++) {
-                    const int sw = s_wsum[w];
-                    if (w < warp) pre += sw;
-                    tot += sw;
-                }
-                int pos = pre + inc - cnt;
-#pragma unroll
-                for (int v = 0; v < MERGE_VT; v++)
-                    if (keep & (1u << v)) s_out[pos++] = ids[v];
-                cn_out = tot;
-            }
-            __syncthreads();
-            for (int k = threadIdx.x; k < cn_out; k += MERGE_THREADS) {  // coalesced write-out
-                const long long pos = o_run + k;
-                if (pos < cap_all) merged[pos] = s_out[k];
-            }
-            o_run += cn_out;
+        for (int k = threadIdx.x; k < cn_out; k += MERGE_THREADS) {  // coalesced write-out
+            const long long pos = o_run + k;
+            if (pos < cap_all) merged[pos] = s_out[k];
         }
+        o_run += cn_out;
+        const int used_a = s_used;
+        a_pos += used_a;
+        b_pos += cn - used_a;
     }
     if (has_len && threadIdx.x == 0) comp_len[(size_t)i * T + t] = (int)(o_run - o0);
 }

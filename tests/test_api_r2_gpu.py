@@ -203,3 +203,48 @@ def test_radius_rule_cuda_1_5_fewer_intersections_same_images():
     for k in ("rgb", "depth", "alpha", "n_contrib"):
         np.testing.assert_array_equal(out[k].cpu().numpy(), ref1[k], err_msg=k)
     r.close()
+
+
+_COMPACT_PROBE = r"""
+import hashlib, json, sys
+import numpy as np
+from sim_a_splat_b200 import scene as S
+from sim_a_splat_b200.renderer import SplatRenderer
+sc = S.make_synthetic_scene(30000, 3, seed=23, link_counts=(900, 500, 200))
+W, H, E = 96, 96, 12
+vms = np.repeat(S.ring_cameras(1, (0, 0, 0), seed=4), E, axis=0)
+r = SplatRenderer(sc, max_images=E, max_envs=E, max_width=W, max_height=H)
+r.set_link_poses(S.random_link_poses(E, 3, seed=31))
+r.set_cameras(vms, S.fov_intrinsics(W, H), W, H, np.arange(E))
+out = r.render(("rgb", "depth", "alpha", "n_contrib"), background=(0.3, 0.1, 0.7))
+h = hashlib.sha256()
+for k in ("rgb", "depth", "alpha", "n_contrib"):
+    h.update(out[k].cpu().numpy().tobytes())
+print(json.dumps({"sha": h.hexdigest(), "n_staged": r.stats()["n_staged"], "n_isects": r.stats()["n_isects"]}))
+"""
+
+
+def test_compacted_compositor_lists_same_bits_fewer_staged_records():
+    """SAS_VARIANT bit 12 (default on): background records that reach none of the groups a tile's link Gaussians can reach
+    are left out of that tile's compositor list.  Against a process with the bit off: fewer staged records, the same
+    images / depth / alpha / contributor counts bit for bit; and the compacted render matches the oracle."""
+    import json, os, subprocess, sys
+    import oracle
+    from parity_utils import assert_parity, compare, run_both
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, var in (("on", "0x12cf"), ("off", "0x2cf")):
+        env = dict(os.environ, SAS_VARIANT=var, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        p = subprocess.run([sys.executable, "-c", _COMPACT_PROBE], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[name] = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["on"]["sha"] == res["off"]["sha"]
+    assert res["on"]["n_isects"] == res["off"]["n_isects"]
+    assert res["on"]["n_staged"] < 0.95 * res["off"]["n_staged"], res
+    # the same shape in this process (whatever SAS_VARIANT it runs under) against the oracle
+    sc = S.make_synthetic_scene(30000, 3, seed=23, link_counts=(900, 500, 200))
+    W, H, E = 96, 96, 12
+    vms = np.repeat(S.ring_cameras(1, (0, 0, 0), seed=4), E, axis=0)
+    gpu, ref = run_both(sc, vms, S.fov_intrinsics(W, H)[None], W, H, S.random_link_poses(E, 3, seed=31), np.arange(E), bg=(0.3, 0.1, 0.7))
+    assert_parity(compare(gpu, ref))

@@ -18,7 +18,7 @@ import subprocess
 import sys
 
 STAGE_OF = [("project_", "project"), ("scan_", "scan"), ("work_", "scan"), ("emit_kernel", "emit"), ("tile_sort_kernel", "sort"),
-            ("merge_", "sort"), ("composite_kernel", "composite"), ("copy_static_tiles", "composite"), ("ns_", "post"),
+            ("merge_", "sort"), ("bg_reach_kernel", "sort"), ("composite_kernel", "composite"), ("copy_static_tiles", "composite"), ("ns_", "post"),
             ("snapshot_kernel", "post"), ("link_pose_kernel", "pose"), ("fk_kernel", "pose")]
 
 
