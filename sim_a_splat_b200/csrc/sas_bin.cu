@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
 
 // bg_reach / tile_dyn_mask / comp_len (all or none): compact the merged list of every image tile to the records the
 // compositor needs (see bg_reach_kernel) and store its length; the ids stay in merged order at the tile's offset.
-__global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
+__global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                               const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
                                                               int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all,
                                                               int fill_static, const int *__restrict__ comp_list,
@@ -284,8 +284,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
                                                               const unsigned *__restrict__ tile_dyn_mask, int *__restrict__ comp_len,
                                                               int compact_max_groups) {
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
-    __shared__ unsigned sr[MERGE_CHUNK];
-    __shared__ int s_out[MERGE_CHUNK];
+    int *const s_out = reinterpret_cast<int *>(sa);  // the merged ids leave through sa once every thread holds its ids in registers
     __shared__ int s_used;
     __shared__ int s_wsum[MERGE_THREADS / 32];
     int t, i;
@@ -336,10 +335,14 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
         const int cn = min(MERGE_CHUNK, n - c * MERGE_CHUNK);
         const int wa = min(cn, na - a_pos), wb = min(cn, nb - b_pos);
         __syncthreads();  // the previous chunk's readers of sa / sb / s_out / s_used are done
-        for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sa[k] = bgp[a_pos + k];
+        for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) {
+            uint2 e = bgp[a_pos + k];
+            // a background record that reaches none of the groups the link Gaussians can reach is not needed: flagged in
+            // the id's top bit (ids are < 2^31)
+            if (compact && (brp[a_pos + k] & dyn) == 0u) e.y |= 0x80000000u;
+            sa[k] = e;
+        }
         for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[b_pos + k];
-        if (compact)
-            for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) sr[k] = brp[a_pos + k];
         __syncthreads();
         const int d = threadIdx.x * MERGE_VT;
         int ids[MERGE_VT];
@@ -353,8 +356,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
                 if (d + v < cn) {
                     const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
                     ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
-                    // a background record that reaches none of the groups the link Gaussians can reach is not needed
-                    if (!compact || !take_a || (sr[ia] & dyn) != 0u) keep |= 1u << v;
+                    if (ids[v] >= 0) keep |= 1u << v;
                     if (take_a) ia++; else ib++;
                 }
             }
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(const uint2 *__res
         }
         int cn_out = cn;
         if (!compact) {
+            __syncthreads();  // s_out aliases sa
 #pragma unroll
             for (int v = 0; v < MERGE_VT; v++)
                 if (keep & (1u << v)) s_out[d + v] = ids[v];
