@@ -217,6 +217,17 @@ void fill_camera(SasCamera &c, const float *vm, const float *K, int width, int h
 
 }  // namespace
 
+// compacted compositor lists are used when a view is shared by at least this many images (SAS_COMPACT_RATIO)
+static int compact_min_ratio() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SAS_COMPACT_RATIO");
+        v = e ? atoi(e) : 4;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
 int sas_variant_flags() {
     static int v = -1;
     if (v < 0) {
@@ -793,7 +804,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
                                      r->fork_ev, &launches));
     // Compacted compositor lists (SAS_VARIANT bit 12): worth it when many images share a view -- the reach masks of the
     // background bucket entries are computed once per VIEW entry and save staging work in every image of the view.
-    const bool compact = (sas_variant_flags() & 0x1000) && (sas_variant_flags() & 8) && (sas_variant_flags() & 2) && r->n_dyn > 0 && I >= 4 * C &&
+    const bool compact = (sas_variant_flags() & 0x1000) && (sas_variant_flags() & 8) && (sas_variant_flags() & 2) && r->n_dyn > 0 && I >= compact_min_ratio() * C &&
                          r->bg_reach.p && r->comp_len.p;
     if (compact) {
         SAS_CUDA(r, sas_launch_bg_reach(pairs, roff, rec, r->n_bg, C, T, tw, cap_src, (unsigned *)r->bg_reach.p, st));
@@ -876,7 +887,7 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
     {   // (bucket, chunk) items of the buckets beyond shared memory: at most one partial chunk per bucket + the full chunks
         const size_t RTb = (size_t)(r->C + r->I) * r->tile_w * r->tile_h;
         if ((rc = ensure(r, r->big_items, (RTb + (size_t)(r->max_isects_src / SAS_SORT_CAP3) + 16) * sizeof(int2)))) return rc;
-        if (r->n_dyn > 0 && r->I >= 4 * r->C) {   // compacted compositor lists (enqueue_render)
+        if (r->n_dyn > 0 && r->I >= compact_min_ratio() * r->C) {   // compacted compositor lists (enqueue_render)
             if ((rc = ensure(r, r->bg_reach, (size_t)r->max_isects_src * 4))) return rc;
             if ((rc = ensure(r, r->comp_len, (size_t)r->I * r->tile_w * r->tile_h * 4))) return rc;
         }
