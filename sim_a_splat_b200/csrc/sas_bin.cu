@@ -255,9 +255,40 @@ __device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB ke
 // compositor: a background record that reaches none of the groups an image tile's link Gaussians can reach cannot touch
 // a pixel composited from that list (the other groups are copied from the view tile), so it is left out -- 28 % of the
 // records of the pusht batch's dynamic tiles.  gridDim.y CTAs per (view, tile) bucket, each a slice of its entries.
+//
+// vrec != nullptr (SAS_VARIANT bit 13): the entry's record is also copied into vrec[k] -- the view bucket's records in
+// depth order, contiguous -- with the reach mask in b.z (b.w = -1 marks it) so that the compositor neither gathers the
+// background records from the view's 5 MB record array nor computes their masks; and because the mask is now computed
+// once per VIEW entry and not once per image, it can afford to be exact: of the groups the culling box reaches only those
+// stay where some pixel centre passes the compositor's own range test (its own sigma expression, sas_refine_reach).
+__device__ __forceinline__ unsigned sas_refine_reach(unsigned m, const float4 A, const float4 B, int tx, int ty) {
+    // alpha = min(0.999, opacity * exp(-sigma)) >= 1/255 needs sigma <= ln(255 opacity); + 0.01 covers logf and the
+    // compositor's polynomial exp.  A negative limit: the Gaussian cannot contribute anywhere.
+    const float lim = fminf(SAS_SIGMA_SKIP, logf(255.0f * B.y) + 0.01f);
+    if (!(lim >= 0.0f)) return 0u;
+    unsigned out = 0u;
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        const int cx = ((bit >> 2) & 1) * 2 + (bit & 1), ry = (bit >> 3) * 2 + ((bit >> 1) & 1);
+        const int x0 = tx * SAS_TILE_PX + 4 * cx, y0 = ty * SAS_TILE_PX + 2 * ry;
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            // exactly blend_one's sigma (sas_composite.cu) at the pixel centre the compositor uses
+            const float pxf = (float)(x0 + (q & 3)) + 0.5f, pyf = (float)(y0 + (q >> 2)) + 0.5f;
+            const float dx = A.x - pxf, dy = A.y - pyf;
+            const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
+            hit = hit || (__float_as_uint(sigma) <= __float_as_uint(lim));
+        }
+        if (hit) out |= 1u << bit;
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                        const SasRecord *__restrict__ rec, int n_bg, int T, int tile_w, long long cap_src,
-                                                       unsigned *__restrict__ bg_reach) {
+                                                       unsigned *__restrict__ bg_reach, SasRecord *__restrict__ vrec) {
     const int vt = blockIdx.x, v = vt / T, t = vt - v * T;
     const int ty = t / tile_w, tx = t - ty * tile_w;
     long long off = row_tile_offset[vt], end = row_tile_offset[vt + 1];
@@ -270,7 +301,14 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
     for (long long k = off + threadIdx.x; k < end; k += 256) {
         const SasRecord *r = rb + pairs[k].y;
         const float4 A = r->a, B = r->b;
-        bg_reach[k] = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+        unsigned m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+        if (vrec) {
+            m = sas_refine_reach(m, A, B, tx, ty);
+            vrec[k].a = A;
+            vrec[k].b = make_float4(B.x, B.y, __uint_as_float(m), -1.0f);
+            vrec[k].c = r->c;
+        }
+        bg_reach[k] = m;
     }
 }
 
@@ -282,7 +320,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
                                                               int fill_static, const int *__restrict__ comp_list,
                                                               const SasWork *__restrict__ work, int I, const unsigned *__restrict__ bg_reach,
                                                               const unsigned *__restrict__ tile_dyn_mask, int *__restrict__ comp_len,
-                                                              int compact_max_groups) {
+                                                              int compact_max_groups, int vrec_codes) {
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
     int *const s_out = reinterpret_cast<int *>(sa);  // the merged ids leave through sa once every thread holds its ids in registers
     __shared__ int s_used;
@@ -337,9 +375,13 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
         __syncthreads();  // the previous chunk's readers of sa / sb / s_out / s_used are done
         for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) {
             uint2 e = bgp[a_pos + k];
-            // a background record that reaches none of the groups the link Gaussians can reach is not needed: flagged in
-            // the id's top bit (ids are < 2^31)
-            if (compact && (brp[a_pos + k] & dyn) == 0u) e.y |= 0x80000000u;
+            if (compact) {
+                // a background record that reaches none of the groups the link Gaussians can reach is not needed: id -1.
+                // vrec_codes: a kept one is named by its position in the view bucket's contiguous records (top bit set;
+                // positions and ids are < 2^31 - 16) instead of its id
+                if ((brp[a_pos + k] & dyn) == 0u) e.y = 0xffffffffu;
+                else if (vrec_codes) e.y = 0x80000000u | (unsigned)(b0 + a_pos + k);
+            }
             sa[k] = e;
         }
         for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[b_pos + k];
@@ -356,7 +398,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
                 if (d + v < cn) {
                     const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
                     ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
-                    if (ids[v] >= 0) keep |= 1u << v;
+                    if (ids[v] != -1) keep |= 1u << v;
                     if (take_a) ia++; else ib++;
                 }
             }
@@ -432,29 +474,29 @@ cudaError_t sas_bin_init() {
 }
 
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
-                                long long cap_src, unsigned *bg_reach, cudaStream_t st) {
+                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, cudaStream_t st) {
     if (C <= 0 || T <= 0) return cudaSuccess;
     // a handful of views x tiles: cut every bucket into slices so that the kernel fills the GPU (36 buckets on the pusht batch)
     const long long buckets = (long long)C * T;
     const unsigned slices = buckets >= 2048 ? 1u : buckets >= 512 ? 4u : 16u;
-    bg_reach_kernel<<<dim3((unsigned)buckets, slices), 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, T, tile_w, cap_src, bg_reach);
+    bg_reach_kernel<<<dim3((unsigned)buckets, slices), 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, T, tile_w, cap_src, bg_reach, vrec);
     return cudaGetLastError();
 }
 
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
                              const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
-                             int *comp_len, cudaStream_t st) {
+                             int *comp_len, int vrec_codes, cudaStream_t st) {
     static int lpt = -1;  // SAS_MERGE_LPT=0: one CTA per (tile, image) in grid order, as for debug fetches
     if (lpt < 0) { const char *e = getenv("SAS_MERGE_LPT"); lpt = e ? atoi(e) : 1; }
     if (comp_list && work && !fill_static && lpt) {
         merge_kernel<<<(unsigned)((long long)(I + C) * T), MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T,
                                                                                  merged_gid, cap_src, cap_all, 0, comp_list, work, I, bg_reach,
-                                                                                 tile_dyn_mask, comp_len, compact_max_groups());
+                                                                                 tile_dyn_mask, comp_len, compact_max_groups(), vrec_codes);
     } else {
         dim3 grid(T, I);
         merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
-                                                     cap_all, fill_static, nullptr, nullptr, I, nullptr, nullptr, nullptr, 32);
+                                                     cap_all, fill_static, nullptr, nullptr, I, nullptr, nullptr, nullptr, 32, 0);
     }
     return cudaGetLastError();
 }

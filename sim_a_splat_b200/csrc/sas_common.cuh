@@ -207,6 +207,9 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //          with expect_tx (UBLKCP / SYNCS in SASS) instead of three 16-byte cp.async (LDGSTS) + wait_group
 //   bit 12 merge: the lists handed to the compositor leave out the background records that reach none of the groups the
 //          tile's link Gaussians can reach (bg_reach_kernel + compaction in merge_kernel); only when images share views
+//   bit 13 (with bit 12) the view buckets' records are materialised in depth order with EXACT reach masks (bg_reach_kernel);
+//          the merged lists name background records by their position there, the compositor stages them from there and
+//          takes their masks as they are
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -289,15 +292,15 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
                              const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
-                             int *comp_len, cudaStream_t st);
+                             int *comp_len, int vrec_codes, cudaStream_t st);
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
-                                long long cap_src, unsigned *bg_reach, cudaStream_t st);
+                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, cudaStream_t st);
 cudaError_t sas_composite_init(int n_sms);
 // Composites the ordered work list (image tiles with link Gaussians + the needed view tiles), then
 // copies the view tiles into the images whose link bucket for that tile is empty.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const unsigned int *tile_dyn_mask, const int *comp_len /*compacted list lengths or null*/,
+                                 const unsigned int *tile_dyn_mask, const int *comp_len /*compacted list lengths or null*/, const SasRecord *vrec /*view bucket records or null*/,
                                  const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,

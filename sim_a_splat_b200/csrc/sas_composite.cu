@@ -380,11 +380,16 @@ __constant__ int sas_variant_flags_dev = 0xff;
 // four per warp, in sas_group_bit order, and the tile becomes ONE CTA of 4 warps (up to 16 packed groups) or TWO (more
 // than 16): a tile with 14 reachable groups keeps 4 warps busy instead of leaving most of 8 warps waiting at the
 // batch barrier while they hold warp slots and registers.  One CTA shape, 16 resident per SM.
-template <int WARPS, int MODE, bool COUNT, bool PACKED = false, bool BULK = false>
+//
+// VREC: background records come from `vrec`, the view buckets' records materialised in depth order with exact reach masks
+// (sas_bin.cu bg_reach_kernel): a merged entry with the top bit set is a position in vrec, a view tile's entry e is
+// vrec[bucket offset + e] (no id list at all), and such a record's mask is taken from its b.z instead of being computed.
+template <int WARPS, int MODE, bool COUNT, bool PACKED = false, bool BULK = false, bool VREC = false>
 __global__ void __launch_bounds__(WARPS * 32, MODE == 3 ? 10 : 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
-                 const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_len, const int *__restrict__ comp_list,
+                 const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_len, const SasRecord *__restrict__ vrec,
+                 const int *__restrict__ comp_list,
                  SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2,
                  SasOutputs img_out, SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, int max_items) {
     constexpr int NT = WARPS * 32;     // threads = records per batch
@@ -434,6 +439,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         int out_img, tile, v;
         const int *gids;   // gid of entry e is gids[e * gstride]
         int gstride, n;
+        unsigned vcode = 0u;   // VREC, view tile: entry e is vrec[vcode & 0x7fffffff + e]
         unsigned dyn_mask = 0xffffffffu;  // bit (warp*4 + group): a link Gaussian of this image can touch the group's 4x2 block
         if (is_view) {
             const long long vt = item - IT;
@@ -446,6 +452,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             gids = reinterpret_cast<const int *>(pairs + off) + 1;  // .y of each (depth, gid) pair
             gstride = 2;
             n = (int)(end - off);
+            vcode = 0x80000000u | (unsigned)off;
         } else {
             out_img = (int)(item / T); tile = (int)(item - (long long)out_img * T);
             v = view_of_image[out_img];
@@ -462,7 +469,8 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         // background records live per view, link records per image; a merged id below n_bg selects the former
         const SasRecord *rec_bg = rec + (size_t)v * n_bg;
         const SasRecord *rec_dy = rec + (size_t)C * n_bg + (size_t)(is_view ? 0 : out_img) * n_dyn - n_bg;
-#define SAS_REC_OF(gid) (((gid) < n_bg ? rec_bg : rec_dy) + (gid))
+#define SAS_REC_OF(gid) (VREC ? ((gid) < 0 ? vrec + ((gid) & 0x7fffffff) : rec_dy + (gid)) : (((gid) < n_bg ? rec_bg : rec_dy) + (gid)))
+#define SAS_GID_AT(e) ((VREC && is_view) ? (int)(vcode + (unsigned)(e)) : __ldg(gids + (size_t)(e) * gstride))
 
         // ---- this lane's pixel ----
         // warp = 8x4 footprint; its four 8-lane groups own the four 4x2 blocks of it (sas_common.cuh: sas_group_bit)
@@ -509,12 +517,12 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         int gid_next = 0;
         if (BULK) {
             if (tid == 0 && n > 0) sas_mbar_expect_tx(&s_mbar[0], (unsigned)min(NT, n) * 48u);
-            if (tid < n) sas_bulk_copy48(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)), &s_mbar[0]);
+            if (tid < n) { const int g0 = SAS_GID_AT(tid); sas_bulk_copy48(&stage[0][tid], SAS_REC_OF(g0), &s_mbar[0]); }
         } else {
-            if (tid < n) stage_record(&stage[0][tid], SAS_REC_OF(__ldg(gids + (size_t)tid * gstride)));
+            if (tid < n) { const int g0 = SAS_GID_AT(tid); stage_record(&stage[0][tid], SAS_REC_OF(g0)); }
             sas_cp_async_commit();
         }
-        if (NT + tid < n) gid_next = __ldg(gids + (size_t)(NT + tid) * gstride);
+        if (NT + tid < n) gid_next = SAS_GID_AT(NT + tid);
         for (int b = 0; b < nb; b++) {
             if (BULK) {   // every thread waits for the whole batch (all bytes landed: the barrier's transaction count is zero)
                 sas_mbar_wait(&s_mbar[b & 1], (mbar_parity >> (b & 1)) & 1u);
@@ -527,7 +535,8 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                 if (b * NT + tid < n) {
                     const float4 A = stage[b & 1][tid].a;
                     const float4 B = stage[b & 1][tid].b;
-                    m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+                    if (VREC && B.w < 0.0f) m = __float_as_uint(B.z);  // a view bucket record: exact mask, precomputed
+                    else m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
                 }
                 s_reach[b & 1][tid] = m;
             }
@@ -546,7 +555,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
                     sas_cp_async_commit();
                 }
                 const int e2 = e1 + NT;
-                if (e2 < n) gid_next = __ldg(gids + (size_t)e2 * gstride);
+                if (e2 < n) gid_next = SAS_GID_AT(e2);
             }
             if (__all_sync(0xffffffffu, p.done())) continue;  // whole warp finished: only keep feeding the pipeline
             if (MODE == 3) process_batch_split<COUNT>(stage[buf], s_reach[buf], (unsigned)warp_arg, cnt, p, s_split[MODE == 3 ? tid >> 5 : 0], s_org[MODE == 3 ? tid >> 5 : 0], split_a_addr, split_c_addr);
@@ -554,6 +563,7 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
         }
         if (!BULK) sas_cp_async_wait<0>();
 #undef SAS_REC_OF
+#undef SAS_GID_AT
 
         if (inside && !group_static) {
             const size_t pi = ((size_t)out_img * H + py) * W + px;
@@ -650,11 +660,11 @@ cudaError_t sas_composite_init(int n_sms) {
 // SAS_VARIANT (sas_common.cuh): bit 0 per-group hit masks, bits 4-5 CTAs per tile.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const unsigned int *tile_dyn_mask, const int *comp_len, const int *comp_list, SasWork *work, int n_bg,
+                                 const unsigned int *tile_dyn_mask, const int *comp_len, const SasRecord *vrec, const int *comp_list, SasWork *work, int n_bg,
                                  int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2,
                                  SasOutputs img_out, SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters,
                                  cudaStream_t st, int *n_launches) {
-#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_len, comp_list, work, n_bg, n_dyn, C, I, W, H, \
+#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_len, vrec, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four
@@ -679,6 +689,9 @@ cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, co
                 } else if (vf & 0x800) {  // bulk-async staging: cp.async.bulk + mbarrier expect_tx instead of LDGSTS + wait_group
                     if (img_out.n_contrib) composite_kernel<4, 2, true, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                     else composite_kernel<4, 2, false, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                } else if (vrec) {  // background records from the view buckets' contiguous copies, exact masks (bit 13)
+                    if (img_out.n_contrib) composite_kernel<4, 2, true, true, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
+                    else composite_kernel<4, 2, false, true, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                 } else if (img_out.n_contrib) composite_kernel<4, 2, true, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
                 else composite_kernel<4, 2, false, true><<<grid4, 128, 0, st>>>(SAS_ARGS);
             } else if (img_out.n_contrib) composite_kernel<8, 2, true><<<grid, 256, 0, st>>>(SAS_ARGS);

@@ -225,7 +225,7 @@ print(json.dumps({"sha": h.hexdigest(), "n_staged": r.stats()["n_staged"], "n_is
 
 
 def test_compacted_compositor_lists_same_bits_fewer_staged_records():
-    """SAS_VARIANT bit 12 (default on): background records that reach none of the groups a tile's link Gaussians can reach
+    """SAS_VARIANT bits 12 and 13 (default on): background records that reach none of the groups a tile's link Gaussians can reach
     are left out of that tile's compositor list.  Against a process with the bit off: fewer staged records, the same
     images / depth / alpha / contributor counts bit for bit; and the compacted render matches the oracle."""
     import json, os, subprocess, sys
@@ -234,14 +234,17 @@ def test_compacted_compositor_lists_same_bits_fewer_staged_records():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for name, var in (("on", "0x12cf"), ("off", "0x2cf")):
+    for name, var in (("on", "0x32cf"), ("ids", "0x12cf"), ("off", "0x2cf")):
         env = dict(os.environ, SAS_VARIANT=var, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
         p = subprocess.run([sys.executable, "-c", _COMPACT_PROBE], env=env, capture_output=True, text=True, timeout=600, cwd=root)
         assert p.returncode == 0, p.stderr[-2000:]
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    assert res["on"]["sha"] == res["off"]["sha"]
-    assert res["on"]["n_isects"] == res["off"]["n_isects"]
-    assert res["on"]["n_staged"] < 0.95 * res["off"]["n_staged"], res
+    # "on": bits 12 + 13 (compacted lists naming the view buckets' contiguous records, exact background reach masks);
+    # "ids": bit 12 alone (compacted id lists, culling-box masks); "off": neither
+    assert res["on"]["sha"] == res["off"]["sha"] and res["ids"]["sha"] == res["off"]["sha"]
+    assert res["on"]["n_isects"] == res["off"]["n_isects"] == res["ids"]["n_isects"]
+    assert res["ids"]["n_staged"] < 0.95 * res["off"]["n_staged"], res
+    assert res["on"]["n_staged"] <= res["ids"]["n_staged"], res      # exact masks can only drop more
     # the same shape in this process (whatever SAS_VARIANT it runs under) against the oracle
     sc = S.make_synthetic_scene(30000, 3, seed=23, link_counts=(900, 500, 200))
     W, H, E = 96, 96, 12
