@@ -811,7 +811,7 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     const bool use_vrec = compact && (vfl & 0x2000) && (vfl & 0xe71) == 0x241 && r->vrec.p;
     SasRecord *vrec = use_vrec ? (SasRecord *)r->vrec.p : nullptr;
     if (compact) {
-        SAS_CUDA(r, sas_launch_bg_reach(pairs, roff, rec, r->n_bg, C, T, tw, cap_src, (unsigned *)r->bg_reach.p, vrec, st));
+        SAS_CUDA(r, sas_launch_bg_reach(pairs, roff, rec, r->n_bg, C, T, tw, cap_src, (unsigned *)r->bg_reach.p, vrec, 0 /* 148 SMs */, st));
         launches += 1;
     }
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, cap_src, cap_all,

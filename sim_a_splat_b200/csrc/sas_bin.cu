@@ -254,7 +254,7 @@ __device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB ke
 // depend on the env, so it is computed once per view entry.  The merge uses it to COMPACT the lists it hands to the
 // compositor: a background record that reaches none of the groups an image tile's link Gaussians can reach cannot touch
 // a pixel composited from that list (the other groups are copied from the view tile), so it is left out -- 28 % of the
-// records of the pusht batch's dynamic tiles.  gridDim.y CTAs per (view, tile) bucket, each a slice of its entries.
+// records of the pusht batch's dynamic tiles.
 //
 // vrec != nullptr (SAS_VARIANT bit 13): the entry's record is also copied into vrec[k] -- the view bucket's records in
 // depth order, contiguous -- with the reach mask in b.z (b.w = -1 marks it) so that the compositor neither gathers the
@@ -266,20 +266,29 @@ __device__ __forceinline__ unsigned sas_refine_reach(unsigned m, const float4 A,
     // compositor's polynomial exp.  A negative limit: the Gaussian cannot contribute anywhere.
     const float lim = fminf(SAS_SIGMA_SKIP, logf(255.0f * B.y) + 0.01f);
     if (!(lim >= 0.0f)) return 0u;
+    const unsigned ulim = __float_as_uint(lim);
+    // centre of the tile's first pixel; every pixel centre below is this plus small integers: exact, and the same float
+    // the compositor forms as (float)px + 0.5f
+    const float X0 = (float)(tx * SAS_TILE_PX) + 0.5f, Y0 = (float)(ty * SAS_TILE_PX) + 0.5f;
+    // exactly blend_one's sigma (sas_composite.cu) and its one-compare range test
+    auto passes = [&](float pxf, float pyf) {
+        const float dx = A.x - pxf, dy = A.y - pyf;
+        const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
+        return __float_as_uint(sigma) <= ulim;
+    };
     unsigned out = 0u;
     while (m) {
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
         const int cx = ((bit >> 2) & 1) * 2 + (bit & 1), ry = (bit >> 3) * 2 + ((bit >> 1) & 1);
-        const int x0 = tx * SAS_TILE_PX + 4 * cx, y0 = ty * SAS_TILE_PX + 2 * ry;
-        bool hit = false;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            // exactly blend_one's sigma (sas_composite.cu) at the pixel centre the compositor uses
-            const float pxf = (float)(x0 + (q & 3)) + 0.5f, pyf = (float)(y0 + (q >> 2)) + 0.5f;
-            const float dx = A.x - pxf, dy = A.y - pyf;
-            const float sigma = fmaf(fmaf(A.z, dx, A.w * dy), dx, (B.x * dy) * dy);
-            hit = hit || (__float_as_uint(sigma) <= __float_as_uint(lim));
+        const float gx = X0 + (float)(4 * cx), gy = Y0 + (float)(2 * ry);  // centre of the group's first pixel
+        // the pixel nearest to the mean first: most reached groups pass there (claiming a hit is always safe, only a miss
+        // must be proven -- by all eight pixels)
+        const float nx = fminf(fmaxf(rintf(A.x - gx), 0.0f), 3.0f), ny = fminf(fmaxf(rintf(A.y - gy), 0.0f), 1.0f);
+        bool hit = passes(gx + nx, gy + ny);
+        if (!hit) {
+#pragma unroll 1
+            for (int q = 0; q < 8 && !hit; q++) hit = passes(gx + (float)(q & 3), gy + (float)(q >> 2));
         }
         if (hit) out |= 1u << bit;
     }
@@ -287,19 +296,22 @@ __device__ __forceinline__ unsigned sas_refine_reach(unsigned m, const float4 A,
 }
 
 __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
-                                                       const SasRecord *__restrict__ rec, int n_bg, int T, int tile_w, long long cap_src,
+                                                       const SasRecord *__restrict__ rec, int n_bg, int CT, int T, int tile_w, long long cap_src,
                                                        unsigned *__restrict__ bg_reach, SasRecord *__restrict__ vrec) {
-    const int vt = blockIdx.x, v = vt / T, t = vt - v * T;
-    const int ty = t / tile_w, tx = t - ty * tile_w;
-    long long off = row_tile_offset[vt], end = row_tile_offset[vt + 1];
-    if (off < 0 || end < off) return;
-    if (end > cap_src) end = cap_src;
-    const SasRecord *rb = rec + (size_t)v * n_bg;
-    const long long slice = (end - off + gridDim.y - 1) / gridDim.y;
-    off += slice * blockIdx.y;
-    if (off + slice < end) end = off + slice;
-    for (long long k = off + threadIdx.x; k < end; k += 256) {
-        const SasRecord *r = rb + pairs[k].y;
+    // The view buckets are the first C*T buckets, i.e. entries [0, row_tile_offset[C*T]) of the pair array.  Flat over the
+    // entries (a grid-stride loop: the count lives on the device), every thread finds its entry's bucket by a binary
+    // search over the offsets -- one CTA per bucket left the 20 000-entry buckets of a 720p view to one CTA each.
+    long long n_view = row_tile_offset[CT];
+    if (n_view > cap_src) n_view = cap_src;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_view; k += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = CT;  // last bucket whose offset is <= k (empty buckets share an offset: the last one holds k)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(row_tile_offset + mid) <= k) lo = mid; else hi = mid;
+        }
+        const int v = lo / T, t = lo - v * T;
+        const int ty = t / tile_w, tx = t - ty * tile_w;
+        const SasRecord *r = rec + (size_t)v * n_bg + pairs[k].y;
         const float4 A = r->a, B = r->b;
         unsigned m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
         if (vrec) {
@@ -474,12 +486,9 @@ cudaError_t sas_bin_init() {
 }
 
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
-                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, cudaStream_t st) {
+                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, int n_sms, cudaStream_t st) {
     if (C <= 0 || T <= 0) return cudaSuccess;
-    // a handful of views x tiles: cut every bucket into slices so that the kernel fills the GPU (36 buckets on the pusht batch)
-    const long long buckets = (long long)C * T;
-    const unsigned slices = buckets >= 2048 ? 1u : buckets >= 512 ? 4u : 16u;
-    bg_reach_kernel<<<dim3((unsigned)buckets, slices), 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, T, tile_w, cap_src, bg_reach, vrec);
+    bg_reach_kernel<<<(n_sms > 0 ? n_sms : 148) * 8, 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, C * T, T, tile_w, cap_src, bg_reach, vrec);
     return cudaGetLastError();
 }
 

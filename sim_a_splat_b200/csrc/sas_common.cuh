@@ -294,7 +294,7 @@ cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, con
                              const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
                              int *comp_len, int vrec_codes, cudaStream_t st);
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
-                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, cudaStream_t st);
+                                long long cap_src, unsigned *bg_reach, SasRecord *vrec, int n_sms, cudaStream_t st);
 cudaError_t sas_composite_init(int n_sms);
 // Composites the ordered work list (image tiles with link Gaussians + the needed view tiles), then
 // copies the view tiles into the images whose link bucket for that tile is empty.
