@@ -261,7 +261,7 @@ __device__ __forceinline__ int merge_path(int d, int na, int nb, KA key_a, KB ke
 // background records from the view's 5 MB record array nor computes their masks; and because the mask is now computed
 // once per VIEW entry and not once per image, it can afford to be exact: of the groups the culling box reaches only those
 // stay where some pixel centre passes the compositor's own range test (its own sigma expression, sas_refine_reach).
-__device__ __forceinline__ unsigned sas_refine_reach(unsigned m, const float4 A, const float4 B, int tx, int ty) {
+__device__ __forceinline__ unsigned sas_refine_reach(unsigned m, const float4 A, const float4 B, int tx, int ty) {  // m: the groups this LANE tests
     // alpha = min(0.999, opacity * exp(-sigma)) >= 1/255 needs sigma <= ln(255 opacity); + 0.01 covers logf and the
     // compositor's polynomial exp.  A negative limit: the Gaussian cannot contribute anywhere.
     const float lim = fminf(SAS_SIGMA_SKIP, logf(255.0f * B.y) + 0.01f);
@@ -301,26 +301,42 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
     // The view buckets are the first C*T buckets, i.e. entries [0, row_tile_offset[C*T]) of the pair array.  Flat over the
     // entries (a grid-stride loop: the count lives on the device), every thread finds its entry's bucket by a binary
     // search over the offsets -- one CTA per bucket left the 20 000-entry buckets of a 720p view to one CTA each.
+    // Eight lanes share an entry (the exact test of a mask's groups is a serial chain: up to 32 groups x 9 sigma
+    // evaluations for a thin Gaussian that crosses the tile): lane j tests the groups whose bit index is j mod 8.
     long long n_view = row_tile_offset[CT];
     if (n_view > cap_src) n_view = cap_src;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_view; k += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = CT;  // last bucket whose offset is <= k (empty buckets share an offset: the last one holds k)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(row_tile_offset + mid) <= k) lo = mid; else hi = mid;
+    const int sub = threadIdx.x & 7;
+    const long long n_iter = (n_view + (long long)gridDim.x * (blockDim.x >> 3) - 1) / ((long long)gridDim.x * (blockDim.x >> 3));
+    for (long long it = 0; it < n_iter; it++) {  // uniform trip count: the shuffles below need the whole warp
+        const long long k = (it * gridDim.x + blockIdx.x) * (blockDim.x >> 3) + (threadIdx.x >> 3);
+        const bool live = k < n_view;
+        unsigned m = 0u;
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+        const SasRecord *r = rec;
+        if (live) {
+            int lo = 0, hi = CT;  // last bucket whose offset is <= k (empty buckets share an offset: the last one holds k)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(row_tile_offset + mid) <= k) lo = mid; else hi = mid;
+            }
+            const int v = lo / T, t = lo - v * T;
+            const int ty = t / tile_w, tx = t - ty * tile_w;
+            r = rec + (size_t)v * n_bg + pairs[k].y;
+            A = r->a; B = r->b;
+            m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
+            if (vrec) m = sas_refine_reach(m & (0x01010101u << sub), A, B, tx, ty);
         }
-        const int v = lo / T, t = lo - v * T;
-        const int ty = t / tile_w, tx = t - ty * tile_w;
-        const SasRecord *r = rec + (size_t)v * n_bg + pairs[k].y;
-        const float4 A = r->a, B = r->b;
-        unsigned m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
-        if (vrec) {
-            m = sas_refine_reach(m, A, B, tx, ty);
-            vrec[k].a = A;
-            vrec[k].b = make_float4(B.x, B.y, __uint_as_float(m), -1.0f);
-            vrec[k].c = r->c;
+        if (vrec) {  // OR over the entry's eight lanes
+            m |= __shfl_xor_sync(0xffffffffu, m, 1);
+            m |= __shfl_xor_sync(0xffffffffu, m, 2);
+            m |= __shfl_xor_sync(0xffffffffu, m, 4);
+            if (live) {  // lanes 0..2 write the three float4 of the record
+                if (sub == 0) vrec[k].a = A;
+                else if (sub == 1) vrec[k].b = make_float4(B.x, B.y, __uint_as_float(m), -1.0f);
+                else if (sub == 2) vrec[k].c = r->c;
+            }
         }
-        bg_reach[k] = m;
+        if (live && sub == 0) bg_reach[k] = m;
     }
 }
 
@@ -488,7 +504,7 @@ cudaError_t sas_bin_init() {
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
                                 long long cap_src, unsigned *bg_reach, SasRecord *vrec, int n_sms, cudaStream_t st) {
     if (C <= 0 || T <= 0) return cudaSuccess;
-    bg_reach_kernel<<<(n_sms > 0 ? n_sms : 148) * 8, 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, C * T, T, tile_w, cap_src, bg_reach, vrec);
+    bg_reach_kernel<<<(n_sms > 0 ? n_sms : 148) * 16, 256, 0, st>>>(pairs, row_tile_offset, rec, n_bg, C * T, T, tile_w, cap_src, bg_reach, vrec);
     return cudaGetLastError();
 }
 

@@ -191,7 +191,7 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
     return xs * e;
 }
 
-// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default 0x12cf):
+// Experiment switches, environment variable SAS_VARIANT (bit mask, read once; default 0x32cf):
 //   bit 0  compositor: per-group (4x2) hit masks instead of one per warp footprint
 //   bit 1  group-level static shortcut (off: every group of a tile with link Gaussians is composited)
 //   bit 2  bucket-sort size classes run on concurrent streams (fork / join on the caller's stream)
