@@ -403,13 +403,12 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
         __syncthreads();  // the previous chunk's readers of sa / sb / s_out / s_used are done
         for (int k = threadIdx.x; k < wa; k += MERGE_THREADS) {
             uint2 e = bgp[a_pos + k];
-            if (compact) {
-                // a background record that reaches none of the groups the link Gaussians can reach is not needed: id -1.
-                // vrec_codes: a kept one is named by its position in the view bucket's contiguous records (top bit set;
-                // positions and ids are < 2^31 - 16) instead of its id
-                if ((brp[a_pos + k] & dyn) == 0u) e.y = 0xffffffffu;
-                else if (vrec_codes) e.y = 0x80000000u | (unsigned)(b0 + a_pos + k);
-            }
+            // a background record that reaches none of the groups the link Gaussians can reach is not needed: id -1.
+            // vrec_codes: the others are named by their position in the view bucket's contiguous records (top bit set;
+            // positions and ids are < 2^31 - 16) instead of their id -- also in a tile the SAS_COMPACT_MAX gate keeps
+            // uncompacted: the compositor reads every background record of this render from vrec
+            if (compact && (brp[a_pos + k] & dyn) == 0u) e.y = 0xffffffffu;
+            else if (vrec_codes) e.y = 0x80000000u | (unsigned)(b0 + a_pos + k);
             sa[k] = e;
         }
         for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[b_pos + k];

@@ -234,14 +234,17 @@ def test_compacted_compositor_lists_same_bits_fewer_staged_records():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for name, var in (("on", "0x32cf"), ("ids", "0x12cf"), ("off", "0x2cf")):
+    for name, var in (("on", "0x32cf"), ("ids", "0x12cf"), ("off", "0x2cf"), ("gate", "0x32cf")):
         env = dict(os.environ, SAS_VARIANT=var, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        if name == "gate":   # the per-tile ablation gate: tiles above 8 reachable groups stay uncompacted, but still name their
+            env["SAS_COMPACT_MAX"] = "8"   # background records by position (a fuzz sweep caught this combination reading ids as positions)
         p = subprocess.run([sys.executable, "-c", _COMPACT_PROBE], env=env, capture_output=True, text=True, timeout=600, cwd=root)
         assert p.returncode == 0, p.stderr[-2000:]
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
     # "on": bits 12 + 13 (compacted lists naming the view buckets' contiguous records, exact background reach masks);
     # "ids": bit 12 alone (compacted id lists, culling-box masks); "off": neither
-    assert res["on"]["sha"] == res["off"]["sha"] and res["ids"]["sha"] == res["off"]["sha"]
+    assert res["on"]["sha"] == res["off"]["sha"] and res["ids"]["sha"] == res["off"]["sha"] and res["gate"]["sha"] == res["off"]["sha"]
+    assert res["on"]["n_staged"] <= res["gate"]["n_staged"] <= res["off"]["n_staged"], res
     assert res["on"]["n_isects"] == res["off"]["n_isects"] == res["ids"]["n_isects"]
     assert res["ids"]["n_staged"] < 0.95 * res["off"]["n_staged"], res
     assert res["on"]["n_staged"] <= res["ids"]["n_staged"], res      # exact masks can only drop more
