@@ -301,14 +301,14 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
     // The view buckets are the first C*T buckets, i.e. entries [0, row_tile_offset[C*T]) of the pair array.  Flat over the
     // entries (a grid-stride loop: the count lives on the device), every thread finds its entry's bucket by a binary
     // search over the offsets -- one CTA per bucket left the 20 000-entry buckets of a 720p view to one CTA each.
-    // Eight lanes share an entry (the exact test of a mask's groups is a serial chain: up to 32 groups x 9 sigma
-    // evaluations for a thin Gaussian that crosses the tile): lane j tests the groups whose bit index is j mod 8.
+    // Four lanes share an entry (the exact test of a mask's groups is a serial chain: up to 32 groups x 9 sigma
+    // evaluations for a thin Gaussian that crosses the tile): lane j tests the groups whose bit index is j mod 4.
     long long n_view = row_tile_offset[CT];
     if (n_view > cap_src) n_view = cap_src;
-    const int sub = threadIdx.x & 7;
-    const long long n_iter = (n_view + (long long)gridDim.x * (blockDim.x >> 3) - 1) / ((long long)gridDim.x * (blockDim.x >> 3));
+    const int sub = threadIdx.x & 3;
+    const long long n_iter = (n_view + (long long)gridDim.x * (blockDim.x >> 2) - 1) / ((long long)gridDim.x * (blockDim.x >> 2));
     for (long long it = 0; it < n_iter; it++) {  // uniform trip count: the shuffles below need the whole warp
-        const long long k = (it * gridDim.x + blockIdx.x) * (blockDim.x >> 3) + (threadIdx.x >> 3);
+        const long long k = (it * gridDim.x + blockIdx.x) * (blockDim.x >> 2) + (threadIdx.x >> 2);
         const bool live = k < n_view;
         unsigned m = 0u;
         float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
@@ -324,12 +324,11 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
             r = rec + (size_t)v * n_bg + pairs[k].y;
             A = r->a; B = r->b;
             m = sas_group_reach_mask(sas_group_reach(make_float4(A.x - B.z, A.x + B.z, A.y - B.w, A.y + B.w)), tx, ty);
-            if (vrec) m = sas_refine_reach(m & (0x01010101u << sub), A, B, tx, ty);
+            if (vrec) m = sas_refine_reach(m & (0x11111111u << sub), A, B, tx, ty);
         }
-        if (vrec) {  // OR over the entry's eight lanes
+        if (vrec) {  // OR over the entry's four lanes
             m |= __shfl_xor_sync(0xffffffffu, m, 1);
             m |= __shfl_xor_sync(0xffffffffu, m, 2);
-            m |= __shfl_xor_sync(0xffffffffu, m, 4);
             if (live) {  // lanes 0..2 write the three float4 of the record
                 if (sub == 0) vrec[k].a = A;
                 else if (sub == 1) vrec[k].b = make_float4(B.x, B.y, __uint_as_float(m), -1.0f);
