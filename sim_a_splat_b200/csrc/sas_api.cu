@@ -311,13 +311,15 @@ int sas_create(const sas_scene_desc *scene, const sas_config *cfg, int device, s
     // background's bounding box, canonical index as the tie-break), link Gaussians as they are.  Measured (round 2b,
     // profiles/r02b_morton_order.txt): emission of the 6 M-Gaussian 1080p chunk 11.8 -> 9.8 ms, but the Gaussians of a CTA
     // then hit the SAME few tiles and serialise on the shared-memory histogram atomics of projection and emission --
-    // configs[2] emission 0.065 -> 0.192 ms, projection 0.080 -> 0.110 ms.  Off by default.
+    // configs[2] emission 0.065 -> 0.192 ms, projection 0.080 -> 0.110 ms.  Default: only for large scenes (below).
     std::vector<int> order(N);
     for (int g = 0; g < N; g++) order[g] = g;
     {
         const char *em = getenv("SAS_MORTON");
         const char *es = getenv("SAS_SORT");
-        const bool want = (em && atoi(em) != 0) && !(es && es[0] == 'b') && n_bg > 1;
+        // unset: on for scenes of 2 M background Gaussians and more (the regime where it was measured to pay)
+        const bool on = em ? atoi(em) != 0 : n_bg >= 2000000;
+        const bool want = on && !(es && es[0] == 'b') && n_bg > 1;
         if (want) {
             float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
             for (int g = 0; g < n_bg; g++)
