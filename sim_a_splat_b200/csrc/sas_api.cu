@@ -53,7 +53,7 @@ struct sas_renderer {
     bool cameras_set = false;
     // grow-only work buffers
     DevBuf rec, bins, row_tile_count, row_tile_cursor, row_tile_offset, img_tile_offset, block_sums, pairs, pairs_alt, merged, img_max;
-    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask, big_items, bg_reach, comp_len, vrec;
+    DevBuf sort_list, comp_list, view_needed, v_acc, v_depth, v_nc, radii, dyn_mask, big_items, bg_reach, comp_len, vrec, merged2;
     SasPoseModel pose_model{};            // device pointers inside; pose_model.L == 0: not set
     double *fk_dev = nullptr;             // [L,15]: fk_R, fk_t, body_offset
     DevBuf body_dev, unproj_d, unproj_xyz, unproj_valid;
@@ -232,7 +232,7 @@ int sas_variant_flags() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SAS_VARIANT");
-        v = e ? (int)strtol(e, nullptr, 0) & 0x3fff : 0x32cf;
+        v = e ? (int)strtol(e, nullptr, 0) & 0x7fff : 0x32cf;
     }
     return v;
 }
@@ -457,7 +457,7 @@ void sas_destroy(sas_renderer *r) {
         if (ev) cudaEventDestroy(ev);
     DevBuf *bufs[] = {&r->rec, &r->bins, &r->row_tile_count, &r->row_tile_cursor, &r->row_tile_offset, &r->img_tile_offset, &r->block_sums,
                       &r->pairs, &r->pairs_alt, &r->merged, &r->img_max, &r->o_rgb[0], &r->o_alpha[0], &r->o_pack[0], &r->o_pack[1],
-                      &r->big_items, &r->bg_reach, &r->comp_len, &r->vrec, &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid,
+                      &r->big_items, &r->bg_reach, &r->comp_len, &r->vrec, &r->merged2, &r->sort_list, &r->comp_list, &r->view_needed, &r->v_acc, &r->v_depth, &r->v_nc, &r->radii, &r->dyn_mask, &r->body_dev, &r->unproj_d, &r->unproj_xyz, &r->unproj_valid,
                       &r->fk_blob, &r->fk_q, &r->fk_extra};
     for (DevBuf *b : bufs) free_buf(*b);
     delete r;
@@ -812,20 +812,23 @@ static int enqueue_render(sas_renderer *r, const sas_outputs *out, float *d_rgb,
     const int vfl = sas_variant_flags();
     const bool use_vrec = compact && (vfl & 0x2000) && (vfl & 0xe71) == 0x241 && r->vrec.p;
     SasRecord *vrec = use_vrec ? (SasRecord *)r->vrec.p : nullptr;
+    // bit 14: per-part lists for tiles composited by two CTAs (flag bits 29 / 30 of the codes: ids and positions below 2^29)
+    const bool use_parts = use_vrec && (vfl & 0x4000) && r->merged2.p && r->max_isects_src < 0x1ffffff0ll && (long long)r->N < 0x1ffffff0ll;
+    int *merged2 = use_parts ? (int *)r->merged2.p : nullptr;
     if (compact) {
         SAS_CUDA(r, sas_launch_bg_reach(pairs, roff, rec, r->n_bg, C, T, tw, cap_src, (unsigned *)r->bg_reach.p, vrec, 0 /* 148 SMs */, st));
         launches += 1;
     }
     SAS_CUDA(r, sas_launch_merge(pairs, roff, ioff, r->view_of_image, C, I, T, merged, cap_src, cap_all,
                                  (sas_variant_flags() & 8) ? 0 : 1, (const int *)r->comp_list.p, work, compact ? (const unsigned *)r->bg_reach.p : nullptr,
-                                 compact ? dyn_mask : nullptr, compact ? (int *)r->comp_len.p : nullptr, use_vrec ? 1 : 0, st));
+                                 compact ? dyn_mask : nullptr, compact ? (int *)r->comp_len.p : nullptr, use_vrec ? 1 : 0, rec, merged2, r->n_bg, r->n_dyn, tw, W, H, st));
     launches += 1;
     SAS_STAGE(4);
     // nerfstudio mode composites over black and blends the background afterwards, like get_outputs does
     const float b0 = ns ? 0.0f : out->background[0], b1 = ns ? 0.0f : out->background[1], b2 = ns ? 0.0f : out->background[2];
     const SasOutputs img_out{d_rgb, d_depth, d_alpha, ns ? nullptr : d_u8, d_nc, d_f16};
     const SasViewBuf view_out{(float *)r->v_acc.p, (float *)r->v_depth.p, (int *)r->v_nc.p};
-    SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, dyn_mask, compact ? (const int *)r->comp_len.p : nullptr, vrec,
+    SAS_CUDA(r, sas_launch_composite(rec, merged, pairs, ioff, roff, rcount, r->view_of_image, dyn_mask, compact ? (const int *)r->comp_len.p : nullptr, vrec, merged2,
                                      (const int *)r->comp_list.p, work,
                                      r->n_bg, r->n_dyn, C, I, W, H, tw, th, b0, b1, b2, img_out, view_out, cap_src, cap_all,
                                      r->counters, st, &launches));
@@ -895,8 +898,9 @@ int sas_render(sas_renderer *r, const sas_outputs *out, void *stream) {
         if ((rc = ensure(r, r->big_items, (RTb + (size_t)(r->max_isects_src / SAS_SORT_CAP3) + 16) * sizeof(int2)))) return rc;
         if (r->n_dyn > 0 && r->I >= compact_min_ratio() * r->C) {   // compacted compositor lists (enqueue_render)
             if ((rc = ensure(r, r->bg_reach, (size_t)r->max_isects_src * 4))) return rc;
-            if ((rc = ensure(r, r->comp_len, (size_t)r->I * r->tile_w * r->tile_h * 4))) return rc;
+            if ((rc = ensure(r, r->comp_len, (size_t)r->I * r->tile_w * r->tile_h * 4 * 2))) return rc;  // part 0 | part 1 lengths
             if ((sas_variant_flags() & 0x2000) && (rc = ensure(r, r->vrec, (size_t)r->max_isects_src * sizeof(SasRecord)))) return rc;
+            if ((sas_variant_flags() & 0x6000) == 0x6000 && (rc = ensure(r, r->merged2, (size_t)r->max_isects * 4))) return rc;
         }
     }
     // the render before last used this staging set: its D2H copy must have drained before the set is overwritten
@@ -1112,7 +1116,7 @@ int sas_debug_fetch(sas_renderer *r, int what, void *dst_host, size_t bytes) {
             // view's bucket); produce them now
             SAS_CUDA(r, sas_launch_merge((const uint2 *)r->pairs.p, (const int *)r->row_tile_offset.p, (const int *)r->img_tile_offset.p,
                                          r->view_of_image, r->C, r->I, (int)T, (int *)r->merged.p, r->max_isects_src, r->max_isects, 1, nullptr, nullptr,
-                                         nullptr, nullptr, nullptr, 0, 0));
+                                         nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0, 0, 0));
             SAS_CUDA(r, cudaDeviceSynchronize());
             src = r->merged.p; avail = (size_t)m * 4;
             break;

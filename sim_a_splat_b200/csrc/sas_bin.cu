@@ -341,15 +341,32 @@ __global__ void __launch_bounds__(256) bg_reach_kernel(const uint2 *__restrict__
 
 // bg_reach / tile_dyn_mask / comp_len (all or none): compact the merged list of every image tile to the records the
 // compositor needs (see bg_reach_kernel) and store its length; the ids stay in merged order at the tile's offset.
+//
+// PARTS (SAS_VARIANT bit 14, with bits 12 + 13): the compositor cuts a tile with more than 16 link-reachable groups into two
+// CTAs ("parts": the first 16 packed groups, the rest), and each used to stage the tile's whole list although a record
+// reaches ~1.5 of a CTA's 16 groups.  Here the merge writes TWO lists, `merged` for part 0 and mp.merged2 for part 1 (same
+// offsets; comp_len[item] and comp_len[I*T + item] entries): a background entry goes to the lists of the parts its exact
+// reach mask (reach pass) touches, a link entry to both.  An entry absent from a part's list could not have been walked by
+// any of its groups, so nothing composited changes.  Codes: bit 31 background (position in vrec), bits 30 / 29 "in part 0 / 1"
+// while in shared memory (cleared on the way out), ids and positions below 2^29.
+struct SasMergeParts {
+    const SasRecord *rec;   // all records (link records of image i: rec + C n_bg + i n_dyn - n_bg, indexed by id)
+    unsigned *reach;        // the reach-mask array of the reach pass (one word per pair position): the link buckets' part is free
+    int *merged2;           // part 1 lists
+    int n_bg, n_dyn, tile_w, W, H;
+};
+
+template <bool PARTS>
 __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *__restrict__ pairs, const int *__restrict__ row_tile_offset,
                                                               const int *__restrict__ img_tile_offset, const int *__restrict__ view_of_image,
                                                               int C, int T, int *__restrict__ merged, long long cap_src, long long cap_all,
                                                               int fill_static, const int *__restrict__ comp_list,
                                                               const SasWork *__restrict__ work, int I, const unsigned *__restrict__ bg_reach,
                                                               const unsigned *__restrict__ tile_dyn_mask, int *__restrict__ comp_len,
-                                                              int compact_max_groups, int vrec_codes) {
+                                                              int compact_max_groups, int vrec_codes, SasMergeParts mp) {
     __shared__ uint2 sa[MERGE_CHUNK], sb[MERGE_CHUNK];
     int *const s_out = reinterpret_cast<int *>(sa);  // the merged ids leave through sa once every thread holds its ids in registers
+    int *const s_out1 = s_out + MERGE_CHUNK;          // PARTS: part 1's ids, the upper half of sa
     __shared__ int s_used;
     __shared__ int s_wsum[MERGE_THREADS / 32];
     int t, i;
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
     const uint2 *bgp = pairs + b0, *dyp = pairs + d0;
     const int n = na + nb;
     const bool has_len = comp_len != nullptr && bg_reach != nullptr && tile_dyn_mask != nullptr;
-    if (nb == 0 || na == 0) {  // only one list (a static tile, or no background here): plain copy
+    if (nb == 0 || (na == 0 && !PARTS)) {  // only one list (a static tile, or no background here): plain copy
         const uint2 *src = nb == 0 ? bgp : dyp;
         for (int k = threadIdx.x; k < n; k += MERGE_THREADS) {
             const long long pos = o0 + k;
@@ -386,9 +403,22 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
     }
     const unsigned dyn = has_len ? tile_dyn_mask[(size_t)i * T + t] : 0xffffffffu;
     // a tile whose link Gaussians reach (nearly) every group drops (nearly) nothing: plain merge, full length
-    const bool compact = has_len && __popc(dyn) <= compact_max_groups;
+    const bool compact = has_len && (PARTS || __popc(dyn) <= compact_max_groups);
     const unsigned *brp = compact ? bg_reach + b0 : nullptr;
     long long o_run = o0;  // compaction: where the next chunk's kept ids go
+    long long o_run1 = o0;  // PARTS: the same for part 1's list (in mp.merged2)
+    // PARTS: the groups of part 0 (the first 16 set bits of the tile's packed-group mask, exactly the compositor's cut)
+    // and of part 1 (the rest; empty for a tile of one CTA)
+    unsigned pm0 = 0u, pm1 = 0u;
+    if (PARTS) {
+        const unsigned pm = dyn & sas_inside_group_mask(t, mp.tile_w, mp.W, mp.H);
+        pm0 = pm;
+        if (__popc(pm) > 16) {
+            const unsigned b16 = __fns(pm, 0u, 16);
+            pm0 = pm & ((2u << b16) - 1u);
+            pm1 = pm & ~pm0;
+        }
+    }
     // Streaming merge: the CTA walks the tile's chunks in order, so it knows where chunk c starts in both lists once
     // chunk c-1 is merged -- no merge-path split search over global memory (a dozen dependent L2 round trips per tile,
     // more than half of a CTA's life in round 1's kernel).  A chunk of cn outputs takes at most cn entries of either
@@ -406,15 +436,26 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
             // vrec_codes: the others are named by their position in the view bucket's contiguous records (top bit set;
             // positions and ids are < 2^31 - 16) instead of their id -- also in a tile the SAS_COMPACT_MAX gate keeps
             // uncompacted: the compositor reads every background record of this render from vrec
-            if (compact && (brp[a_pos + k] & dyn) == 0u) e.y = 0xffffffffu;
+            if (PARTS) {
+                const unsigned m = brp[a_pos + k];
+                const unsigned f = ((m & pm0) ? 0x40000000u : 0u) | ((m & pm1) ? 0x20000000u : 0u);
+                e.y = f ? (0x80000000u | f | (unsigned)(b0 + a_pos + k)) : 0xffffffffu;
+            } else if (compact && (brp[a_pos + k] & dyn) == 0u) e.y = 0xffffffffu;
             else if (vrec_codes) e.y = 0x80000000u | (unsigned)(b0 + a_pos + k);
             sa[k] = e;
         }
-        for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) sb[k] = dyp[b_pos + k];
+        for (int k = threadIdx.x; k < wb; k += MERGE_THREADS) {
+            uint2 e = dyp[b_pos + k];
+            // link entries go to both lists: their masks would have to be gathered from the link records (measured: 660 MB
+            // of L2 traffic and a latency-bound merge, 0.09 -> 0.24 ms, against 0.04 ms saved in the compositor)
+            if (PARTS) e.y |= pm1 ? 0x60000000u : 0x40000000u;
+            sb[k] = e;
+        }
         __syncthreads();
         const int d = threadIdx.x * MERGE_VT;
         int ids[MERGE_VT];
-        unsigned keep = 0u;  // bit v: output d + v exists and is kept
+        unsigned keep = 0u;  // bit v: output d + v exists and is kept (PARTS: in part 0's list)
+        unsigned keep1 = 0u;  // PARTS: ... in part 1's list
         if (d < cn) {
             int ia = merge_path(d, wa, wb, [&](int k) { return sa[k].x; }, [&](int k) { return sb[k].x; });
             int ib = d - ia;
@@ -424,20 +465,28 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
                 if (d + v < cn) {
                     const bool take_a = ib >= wb || (ia < wa && sa[ia].x <= sb[ib].x);
                     ids[v] = (int)(take_a ? sa[ia].y : sb[ib].y);
-                    if (ids[v] != -1) keep |= 1u << v;
+                    if (PARTS) {
+                        const unsigned cd = (unsigned)ids[v];
+                        if (cd != 0xffffffffu) {
+                            keep |= ((cd >> 30) & 1u) << v;
+                            keep1 |= ((cd >> 29) & 1u) << v;
+                            ids[v] = (int)(cd & 0x9fffffffu);
+                        }
+                    } else if (ids[v] != -1) keep |= 1u << v;
                     if (take_a) ia++; else ib++;
                 }
             }
             if (d + MERGE_VT >= cn) s_used = ia;  // the thread that merges the chunk's last output: background entries used
         }
-        int cn_out = cn;
+        int cn_out = cn, cn_out1 = 0;
         if (!compact) {
             __syncthreads();  // s_out aliases sa
 #pragma unroll
             for (int v = 0; v < MERGE_VT; v++)
                 if (keep & (1u << v)) s_out[d + v] = ids[v];
         } else {  // exclusive scan of the kept counts over the CTA, then every thread writes its kept ids densely
-            const int cnt = __popc(keep), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            // PARTS: both lists' counts in one word (part 1's in the upper half; a chunk holds 1 024 entries)
+            const int cnt = __popc(keep) | (PARTS ? __popc(keep1) << 16 : 0), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             int inc = cnt;
 #pragma unroll
             for (int s_ = 1; s_ < 32; s_ <<= 1) {
@@ -453,11 +502,14 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
                 if (w < warp) pre += sw;
                 tot += sw;
             }
-            int pos = pre + inc - cnt;
+            int pos = (pre + inc - cnt) & 0xffff, pos1 = (pre + inc - cnt) >> 16;
 #pragma unroll
-            for (int v = 0; v < MERGE_VT; v++)
+            for (int v = 0; v < MERGE_VT; v++) {
                 if (keep & (1u << v)) s_out[pos++] = ids[v];
-            cn_out = tot;
+                if (PARTS && (keep1 & (1u << v))) s_out1[pos1++] = ids[v];
+            }
+            cn_out = tot & 0xffff;
+            cn_out1 = tot >> 16;
         }
         __syncthreads();
         for (int k = threadIdx.x; k < cn_out; k += MERGE_THREADS) {  // coalesced write-out
@@ -465,11 +517,21 @@ __global__ void __launch_bounds__(MERGE_THREADS, 12) merge_kernel(const uint2 *_
             if (pos < cap_all) merged[pos] = s_out[k];
         }
         o_run += cn_out;
+        if (PARTS) {
+            for (int k = threadIdx.x; k < cn_out1; k += MERGE_THREADS) {
+                const long long pos = o_run1 + k;
+                if (pos < cap_all) mp.merged2[pos] = s_out1[k];
+            }
+            o_run1 += cn_out1;
+        }
         const int used_a = s_used;
         a_pos += used_a;
         b_pos += cn - used_a;
     }
-    if (has_len && threadIdx.x == 0) comp_len[(size_t)i * T + t] = (int)(o_run - o0);
+    if (has_len && threadIdx.x == 0) {
+        comp_len[(size_t)i * T + t] = (int)(o_run - o0);
+        if (PARTS) comp_len[(size_t)I * T + (size_t)i * T + t] = (int)(o_run1 - o0);
+    }
 }
 
 }  // namespace
@@ -509,17 +571,25 @@ cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, 
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
                              const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
-                             int *comp_len, int vrec_codes, cudaStream_t st) {
+                             int *comp_len, int vrec_codes, const SasRecord *rec, int *merged2, int n_bg, int n_dyn, int tile_w, int W,
+                             int H, cudaStream_t st) {
     static int lpt = -1;  // SAS_MERGE_LPT=0: one CTA per (tile, image) in grid order, as for debug fetches
     if (lpt < 0) { const char *e = getenv("SAS_MERGE_LPT"); lpt = e ? atoi(e) : 1; }
+    const SasMergeParts mp{rec, const_cast<unsigned *>(bg_reach), merged2, n_bg, n_dyn, tile_w, W, H};
     if (comp_list && work && !fill_static && lpt) {
-        merge_kernel<<<(unsigned)((long long)(I + C) * T), MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T,
-                                                                                 merged_gid, cap_src, cap_all, 0, comp_list, work, I, bg_reach,
-                                                                                 tile_dyn_mask, comp_len, compact_max_groups(), vrec_codes);
+        const unsigned grid = (unsigned)((long long)(I + C) * T);
+        if (merged2 && rec && comp_len && bg_reach && tile_dyn_mask && vrec_codes)
+            merge_kernel<true><<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
+                                                               cap_all, 0, comp_list, work, I, bg_reach, tile_dyn_mask, comp_len,
+                                                               compact_max_groups(), vrec_codes, mp);
+        else
+            merge_kernel<false><<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
+                                                                cap_all, 0, comp_list, work, I, bg_reach, tile_dyn_mask, comp_len,
+                                                                compact_max_groups(), vrec_codes, mp);
     } else {
         dim3 grid(T, I);
-        merge_kernel<<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
-                                                     cap_all, fill_static, nullptr, nullptr, I, nullptr, nullptr, nullptr, 32, 0);
+        merge_kernel<false><<<grid, MERGE_THREADS, 0, st>>>(pairs, row_tile_offset, img_tile_offset, view_of_image, C, T, merged_gid, cap_src,
+                                                            cap_all, fill_static, nullptr, nullptr, I, nullptr, nullptr, nullptr, 32, 0, mp);
     }
     return cudaGetLastError();
 }

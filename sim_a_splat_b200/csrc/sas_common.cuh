@@ -210,6 +210,9 @@ __device__ __forceinline__ unsigned sas_group_reach_mask(const SasGroupReach g, 
 //   bit 13 (with bit 12) the view buckets' records are materialised in depth order with EXACT reach masks (bg_reach_kernel);
 //          the merged lists name background records by their position there, the compositor stages them from there and
 //          takes their masks as they are
+//   bit 14 (with bits 12 + 13; ablation, off) a tile composited by two CTAs gets TWO lists (merge_kernel<true>): a background
+//          entry goes to the list of the CTA(s) whose groups its exact mask touches, a link entry to both -- instead of both
+//          CTAs staging the whole list.  Measured +1 % on the pusht batch, -1.4 % on the configs[3] shard
 //   bits 4-5  compositor CTAs per tile: 0 = one (8 warps), 1 = two (4 warps each), 2-3 = four (2 warps each)
 int sas_variant_flags();
 
@@ -292,7 +295,8 @@ cudaError_t sas_launch_tile_sort(uint2 *pairs, uint2 *pairs_alt, const int *row_
 cudaError_t sas_launch_merge(const uint2 *pairs, const int *row_tile_offset, const int *img_tile_offset, const int *view_of_image,
                              int C, int I, int T, int *merged_gid, long long cap_src, long long cap_all, int fill_static,
                              const int *comp_list, const SasWork *work, const unsigned *bg_reach, const unsigned *tile_dyn_mask,
-                             int *comp_len, int vrec_codes, cudaStream_t st);
+                             int *comp_len, int vrec_codes, const SasRecord *rec, int *merged2 /*part-1 lists or null*/, int n_bg, int n_dyn,
+                             int tile_w, int W, int H, cudaStream_t st);
 cudaError_t sas_launch_bg_reach(const uint2 *pairs, const int *row_tile_offset, const SasRecord *rec, int n_bg, int C, int T, int tile_w,
                                 long long cap_src, unsigned *bg_reach, SasRecord *vrec, int n_sms, cudaStream_t st);
 cudaError_t sas_composite_init(int n_sms);
@@ -300,7 +304,7 @@ cudaError_t sas_composite_init(int n_sms);
 // copies the view tiles into the images whose link bucket for that tile is empty.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const unsigned int *tile_dyn_mask, const int *comp_len /*compacted list lengths or null*/, const SasRecord *vrec /*view bucket records or null*/,
+                                 const unsigned int *tile_dyn_mask, const int *comp_len /*compacted list lengths or null*/, const SasRecord *vrec /*view bucket records or null*/, const int *merged2 /*part-1 lists or null*/,
                                  const int *comp_list, SasWork *work, int n_bg, int n_dyn, int C,
                                  int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2, SasOutputs img_out,
                                  SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, cudaStream_t st,

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(WARPS * 32, MODE == 3 ? 10 : 64 / WARPS)
 composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merged_gid, const uint2 *__restrict__ pairs,
                  const int *__restrict__ img_tile_offset, const int *__restrict__ row_tile_offset, const int *__restrict__ view_of_image,
                  const unsigned int *__restrict__ tile_dyn_mask, const int *__restrict__ comp_len, const SasRecord *__restrict__ vrec,
-                 const int *__restrict__ comp_list,
+                 const int *__restrict__ merged2, const int *__restrict__ comp_list,
                  SasWork *work, int n_bg, int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2,
                  SasOutputs img_out, SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters, int max_items) {
     constexpr int NT = WARPS * 32;     // threads = records per batch
@@ -460,10 +460,12 @@ composite_kernel(const SasRecord *__restrict__ rec, const int *__restrict__ merg
             if (off < 0 || end < off) { off = 0; end = 0; }
             if (end > cap_all) end = cap_all;
             if (off > end) off = end;
-            gids = merged_gid + off;
+            // merged2 (VREC only): the tile's second CTA has a list of its own -- the entries that reach one of ITS groups
+            const bool second = VREC && merged2 != nullptr && (k % PARTS) == 1u;
+            gids = (second ? merged2 : merged_gid) + off;
             gstride = 1;
             n = (int)(end - off);
-            if (comp_len) n = min(n, __ldg(comp_len + item));  // the merge left out records no composited group can see
+            if (comp_len) n = min(n, __ldg(comp_len + (second ? IT : 0ll) + item));  // the merge left out records no composited group can see
             dyn_mask = tile_dyn_mask[item];
         }
         // background records live per view, link records per image; a merged id below n_bg selects the former
@@ -660,11 +662,11 @@ cudaError_t sas_composite_init(int n_sms) {
 // SAS_VARIANT (sas_common.cuh): bit 0 per-group hit masks, bits 4-5 CTAs per tile.
 cudaError_t sas_launch_composite(const SasRecord *rec, const int *merged_gid, const uint2 *pairs, const int *img_tile_offset,
                                  const int *row_tile_offset, const unsigned int *row_tile_count, const int *view_of_image,
-                                 const unsigned int *tile_dyn_mask, const int *comp_len, const SasRecord *vrec, const int *comp_list, SasWork *work, int n_bg,
+                                 const unsigned int *tile_dyn_mask, const int *comp_len, const SasRecord *vrec, const int *merged2, const int *comp_list, SasWork *work, int n_bg,
                                  int n_dyn, int C, int I, int W, int H, int tile_w, int tile_h, float bg0, float bg1, float bg2,
                                  SasOutputs img_out, SasViewBuf view_out, long long cap_src, long long cap_all, SasCounters *counters,
                                  cudaStream_t st, int *n_launches) {
-#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_len, vrec, comp_list, work, n_bg, n_dyn, C, I, W, H, \
+#define SAS_ARGS rec, merged_gid, pairs, img_tile_offset, row_tile_offset, view_of_image, tile_dyn_mask, comp_len, vrec, merged2, comp_list, work, n_bg, n_dyn, C, I, W, H, \
                  tile_w, tile_h, bg0, bg1, bg2, img_out, view_out, cap_src, cap_all, counters, max_items
     const int vf = sas_variant_flags();
     const int parts = (vf >> 4) & 3;  // 0: one CTA per tile, 1: two, 2 or 3: four

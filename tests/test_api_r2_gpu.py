@@ -225,7 +225,7 @@ print(json.dumps({"sha": h.hexdigest(), "n_staged": r.stats()["n_staged"], "n_is
 
 
 def test_compacted_compositor_lists_same_bits_fewer_staged_records():
-    """SAS_VARIANT bits 12 and 13 (default on): background records that reach none of the groups a tile's link Gaussians can reach
+    """SAS_VARIANT bits 12 and 13 (default on) and 14 (ablation): background records that reach none of the groups a tile's link Gaussians can reach
     are left out of that tile's compositor list.  Against a process with the bit off: fewer staged records, the same
     images / depth / alpha / contributor counts bit for bit; and the compacted render matches the oracle."""
     import json, os, subprocess, sys
@@ -234,20 +234,23 @@ def test_compacted_compositor_lists_same_bits_fewer_staged_records():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for name, var in (("on", "0x32cf"), ("ids", "0x12cf"), ("off", "0x2cf"), ("gate", "0x32cf")):
+    for name, var in (("on", "0x72cf"), ("vrec", "0x32cf"), ("ids", "0x12cf"), ("off", "0x2cf"), ("gate", "0x32cf")):
         env = dict(os.environ, SAS_VARIANT=var, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
         if name == "gate":   # the per-tile ablation gate: tiles above 8 reachable groups stay uncompacted, but still name their
             env["SAS_COMPACT_MAX"] = "8"   # background records by position (a fuzz sweep caught this combination reading ids as positions)
         p = subprocess.run([sys.executable, "-c", _COMPACT_PROBE], env=env, capture_output=True, text=True, timeout=600, cwd=root)
         assert p.returncode == 0, p.stderr[-2000:]
         res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    # "on": bits 12 + 13 (compacted lists naming the view buckets' contiguous records, exact background reach masks);
-    # "ids": bit 12 alone (compacted id lists, culling-box masks); "off": neither
-    assert res["on"]["sha"] == res["off"]["sha"] and res["ids"]["sha"] == res["off"]["sha"] and res["gate"]["sha"] == res["off"]["sha"]
-    assert res["on"]["n_staged"] <= res["gate"]["n_staged"] <= res["off"]["n_staged"], res
-    assert res["on"]["n_isects"] == res["off"]["n_isects"] == res["ids"]["n_isects"]
+    # "on": bits 12 + 13 + 14 (the ablation with a list of its own for each of the two CTAs of a tile with more than 16 groups);
+    # "vrec": bits 12 + 13 (compacted lists naming the view buckets' contiguous records, exact background reach masks);
+    # "ids": bit 12 alone (compacted id lists, culling-box masks); "off": none of them
+    for k in ("on", "vrec", "ids", "gate"):
+        assert res[k]["sha"] == res["off"]["sha"], k
+    assert res["vrec"]["n_staged"] <= res["gate"]["n_staged"] <= res["off"]["n_staged"], res
+    assert res["on"]["n_isects"] == res["off"]["n_isects"] == res["ids"]["n_isects"] == res["vrec"]["n_isects"]
     assert res["ids"]["n_staged"] < 0.95 * res["off"]["n_staged"], res
-    assert res["on"]["n_staged"] <= res["ids"]["n_staged"], res      # exact masks can only drop more
+    assert res["vrec"]["n_staged"] <= res["ids"]["n_staged"], res      # exact masks can only drop more
+    assert res["on"]["n_staged"] <= res["vrec"]["n_staged"], res       # a part's list is a subset of the tile's
     # the same shape in this process (whatever SAS_VARIANT it runs under) against the oracle
     sc = S.make_synthetic_scene(30000, 3, seed=23, link_counts=(900, 500, 200))
     W, H, E = 96, 96, 12
